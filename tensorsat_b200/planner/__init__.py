@@ -1,0 +1,14 @@
+"""Host-side planning: flat networks, contraction trees, slicing (not on the timed path)."""
+
+from .network import Network
+from .search import find_tree
+from .tree import ContractionTree, TreeStats, linear_to_ssa, ssa_to_linear
+
+__all__ = [
+    "Network",
+    "ContractionTree",
+    "TreeStats",
+    "find_tree",
+    "linear_to_ssa",
+    "ssa_to_linear",
+]
