@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""
+bench.py — contraction-phase benchmark of the B200 executor (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (every N): BASELINE config 1, random 3-SAT n=50 m=213 (ratio 4.26) seed 0, SAT decision
+with all inputs unknown, the reference's bintree network (1008 leaf tensors, 795 wires); an
+elimination-order contraction tree sliced to 2^28-entry intermediates = 64 slices.  A "step" is
+one whole contraction (shared part + all 64 slices + combine); with N GPUs the 64 slices are split
+into contiguous blocks, one per rank, and combined by one NCCL all-reduce (max).  Total work is
+fixed, so scaling is "strong"; the metric is the contraction time in seconds.
+
+Timed region: leaves resident in HBM, K executions bracketed by barrier + synchronize, CUDA events
+on the launching stream, max over ranks.  Every intermediate of a slice is far larger than L2
+(126 MB), so successive steps cannot hit in L2.  ``e2e`` times the same contraction through
+``TreeContraction.contract_from_host`` with the leaves in host memory (one H2D of the packed
+leaves and one D2H of the verdict inside the timed region).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_VARS, N_CLAUSES, SEED, K_SAT = 50, 213, 0, 3
+TARGET_LOG2 = 28
+PLAN_FILE = os.path.join(ROOT, "bench_plans", "c1_n50_m213_seed0.json")
+WORKLOAD = (f"random {K_SAT}-SAT n={N_VARS} m={N_CLAUSES} seed={SEED}, SAT decision (all inputs unknown), "
+            f"bintree network, elimination-order tree sliced to 2^{TARGET_LOG2}-entry intermediates")
+
+
+def load_tree():
+    from tensorsat_b200.lib.sat import CNFInstance
+    from tensorsat_b200.planner import ContractionTree, Network
+    from tensorsat_b200.planner.search import find_tree_elimination
+
+    cnf = CNFInstance.random(K_SAT, N_VARS, N_CLAUSES, rng=SEED)
+    diagram = (cnf.inputs(None) >> cnf.diagram()).flatten()
+    net = Network.from_diagram(diagram)
+    tree = None
+    if os.path.exists(PLAN_FILE):
+        with open(PLAN_FILE) as f:
+            tree = ContractionTree.from_json(json.load(f))
+        if tree.network != net:
+            tree = None
+    if tree is None:
+        tree = find_tree_elimination(net, trials=12, seed=0).slice_to(TARGET_LOG2)
+        try:
+            os.makedirs(os.path.dirname(PLAN_FILE), exist_ok=True)
+            with open(PLAN_FILE, "w") as f:
+                f.write(tree.dumps())
+        except OSError:
+            pass
+    return cnf, diagram, tree
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        assert self.proc and self.proc.stdout
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22) -> dict:
+    """The reference arithmetic (numpy oracle) on a bounded sample of the same plan: the tree is sliced
+    further so that one slice fits the host comfortably, `n_sample` slices are timed and the whole-job
+    time is extrapolated (slices have identical shapes and cost)."""
+    from oracle import fin_rel_oracle as O
+
+    fine = tree.with_sliced(()).slice_to(target_log2)
+    leaves = [b.tensor for b in diagram.boxes]
+    n = fine.num_slices
+    ids = [int(i * n / n_sample) for i in range(n_sample)]
+    net = fine.network
+    O.execute_tree(net.inputs, net.output, leaves, fine.ssa_path, fine.sliced_wires, slice_ids=ids[:1], size_dict=net.size_dict)
+    t0 = time.perf_counter()
+    O.execute_tree(net.inputs, net.output, leaves, fine.ssa_path, fine.sliced_wires, slice_ids=ids, size_dict=net.size_dict)
+    dt = time.perf_counter() - t0
+    est = dt / n_sample * n
+    return {"value": est, "unit": "s", "cores": 1, "kind": "port",
+            "host_cores_available": os.cpu_count(),
+            "sample": (f"numpy oracle (reference arithmetic, single-threaded integer einsum) on {n_sample} of {n} slices "
+                       f"of the same tree sliced to 2^{target_log2}-entry intermediates, {dt:.2f} s measured, "
+                       f"extrapolated x{n / n_sample:.0f}")}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cnf, diagram, tree = load_tree()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(tree, diagram, n_sample=4)
+        if i >= args.warmup:
+            vals.append(r)
+    v = sum(x["value"] for x in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "random 3-SAT contraction time", "value": v, "unit": "s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_slices": tree.num_slices},
+        "cpu_baseline": {**vals[-1], "value": v},
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tensorsat_b200 import _native
+    from tensorsat_b200.contractions.tree import TreeContraction
+    from tensorsat_b200.distributed import all_reduce_result, slice_block
+    from tensorsat_b200.lang.fin_rel import CudaFinRel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cnf, diagram, tree = load_tree()
+    contraction = TreeContraction(CudaFinRel, diagram.wiring, tree=tree)
+    plan = contraction.plan()
+    n_slices = plan.info["n_slices"]
+    lo, hi = slice_block(n_slices, rank, world)
+    leaves_dev = [contraction._leaf_tensor(b) for b in diagram.boxes]
+    out = _native.empty(plan.info["out_numel"], contraction.mode)
+
+    def step() -> None:
+        plan.execute(leaves_dev, out, lo, hi)
+        if world > 1:
+            all_reduce_result(out, contraction.mode)
+
+    def sync_all() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    verdict = bool(out.cpu().numpy().reshape(-1)[0])
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = ms / args.steps
+
+    # ---- end to end through the public API with HOST leaf buffers
+    leaves_host = [b.tensor for b in diagram.boxes]
+    for _ in range(2):
+        contraction.contract_from_host(leaves_host, (lo, hi))
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = contraction.contract_from_host(leaves_host, (lo, hi))
+        if world > 1:
+            r = torch.from_numpy(res.reshape(-1).copy()).cuda()
+            all_reduce_result(r, contraction.mode)
+            res = r.cpu().numpy()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+
+    # ---- per-kernel roofline: instrumented pass (CUDA events around every launch of the plan)
+    roof = None
+    if rank == 0:
+        plan.set_timing(True)
+        plan.execute(leaves_dev, out, lo, hi)
+        torch.cuda.synchronize()
+        desc = plan.describe()
+        plan.set_timing(False)
+        peak, peak_src = hbm_peak()
+        share = (hi - lo) if n_slices > 1 else 1
+        merge = [o for o in desc["ops"] if o["kind"] == "merge"]
+        mbytes = sum(o["bytes"] * (share if o["per_slice"] else 1) for o in merge)
+        mms = sum(o["ms"] for o in merge)
+        all_ms = sum(o["ms"] for o in desc["ops"])
+        n_launch = sum((share if o["per_slice"] else 1) for o in merge)
+        achieved = mbytes / (mms * 1e-3) / 1e9 if mms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "merge_traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "k_merge<u8,u8,u8,clamp>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": mbytes / max(n_launch, 1), "avg_launch_ms": mms / max(n_launch, 1),
+                "launches_per_step": n_launch, "share_of_step": mms / all_ms if all_ms else None,
+                "whole_step_alg_GBps": (plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * share)
+                / (ms_per_step * 1e-3) / 1e9}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_sample(tree, diagram, n_sample=16)
+        line = {
+            "metric": "random 3-SAT contraction time", "value": ms_per_step * 1e-3, "unit": "s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_slices": int(n_slices), "slices_per_rank": int(hi - lo),
+                       "verdict": "SAT" if verdict else "UNSAT", "l2": "inputs larger than L2",
+                       "peak_arena_bytes": int(plan.info["peak_bytes"]), "kernels_per_step": launches // max(args.steps, 1),
+                       "alg_bytes_per_step": plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n_slices},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": contraction.h2d_bytes,
+                    "d2h_bytes_per_step": contraction.d2h_bytes},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

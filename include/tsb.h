@@ -1,0 +1,199 @@
+/*
+ * tsb.h — C-ABI of libtsb.so, the B200 (sm_100a) contraction executor for TensorSat.
+ *
+ * Drop-in boundary.  The reference has no native code; each entry point
+ * below replaces the numeric body of one reference function (paths relative to the
+ * reference repository), and is what a binding for that function would call:
+ *
+ *   tsb_contract2      FinRel._contract2              tensorsat/lang/fin_rel.py:255-288
+ *                      (+ _to_safe_contraction_dtype  tensorsat/lang/fin_rel.py:145-159)
+ *   tsb_rewire         FinRel._rewire / rewire_array  tensorsat/lang/fin_rel.py:379-393,
+ *                                                     tensorsat/_utils/misc.py:104-123
+ *   tsb_permute        np.transpose materialisation   tensorsat/lang/fin_rel.py:381-382
+ *   tsb_slice          FinRel._getitem                tensorsat/lang/fin_rel.py:342-343
+ *   tsb_union          FinRel._union                  tensorsat/lang/fin_rel.py:345-346
+ *   tsb_stack          FinRel._stack                  tensorsat/lang/fin_rel.py:304-308
+ *   tsb_spider         FinRel._spider / _scalar       tensorsat/lang/fin_rel.py:290-302
+ *   tsb_all_ones       FinRel._as_scalar              tensorsat/lang/fin_rel.py:472-473
+ *   tsb_plan_*         ContractionTree.contract as driven by
+ *                      CotengraContraction.contract   tensorsat/contractions/cotengra.py:100-128
+ *                      and SimpleContraction.contract tensorsat/contractions/simple.py:251-292
+ *   tsb_arena_*        per-step numpy allocations     tensorsat/lang/fin_rel.py:310-326
+ *
+ * Conventions
+ *   - Every function returns a tsb_status (0 = ok) and never throws; tsb_last_error()
+ *     returns a thread-local message for the last failing call on this thread.
+ *   - Tensors are dense, C-ordered (last axis fastest), caller-owned DEVICE buffers
+ *     (e.g. torch storage) unless obtained from the arena.  No torch types cross the ABI.
+ *   - All work is enqueued on the caller-supplied stream (a cudaStream_t passed as
+ *     void*); the only synchronising calls are tsb_all_ones and tsb_scalar_to_host.
+ *   - A context is bound to one device and is not thread-safe; distinct contexts may be
+ *     used concurrently (one per rank / process).
+ *   - Wires are small non-negative integers < n_wires; wire_extents[w] is the dimension of
+ *     wire w.  Power-of-two extents take the fast kernels, anything else a generic one.
+ *   - mode TSB_SAT clamps every result to {0,1} (boolean semiring, count > 0);
+ *     TSB_COUNT accumulates exactly (counting semiring).
+ */
+#ifndef TSB_H_
+#define TSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSB_VERSION 100 /* 0.1.0 */
+#define TSB_MAX_RANK 62
+
+typedef struct tsb_ctx tsb_ctx;
+typedef struct tsb_plan tsb_plan;
+typedef void* tsb_stream; /* cudaStream_t */
+
+typedef enum {
+  TSB_OK = 0,
+  TSB_ERR_INVALID = 1,     /* contract violation (ValueError on the Python side) */
+  TSB_ERR_CUDA = 2,        /* CUDA runtime / driver error */
+  TSB_ERR_OOM = 3,         /* device allocation failed */
+  TSB_ERR_UNSUPPORTED = 4, /* valid but not implemented */
+  TSB_ERR_OVERFLOW = 5     /* counting result may not fit in int64 */
+} tsb_status;
+
+typedef enum { TSB_U8 = 0, TSB_I32 = 1, TSB_I64 = 2 } tsb_dtype;
+typedef enum { TSB_SAT = 0, TSB_COUNT = 1 } tsb_mode;
+
+int tsb_version(void);
+const char* tsb_last_error(void);
+
+int tsb_ctx_create(int device, tsb_ctx** ctx);
+int tsb_ctx_destroy(tsb_ctx* ctx);
+/* Number of kernels launched through this context since creation (bench "gpu_launches"). */
+int tsb_ctx_launch_count(tsb_ctx* ctx, int64_t* count);
+
+/* ---- caching device allocator for intermediates (north-star item (d)) ------------------- */
+typedef struct {
+  size_t reserved_bytes;    /* device memory held by the arena */
+  size_t in_use_bytes;      /* handed out and not yet released */
+  size_t peak_in_use_bytes; /* high-water mark of in_use_bytes */
+  size_t device_allocs;     /* number of cudaMalloc calls so far */
+  size_t cache_hits;        /* allocations served without touching the driver */
+} tsb_arena_stats_t;
+
+int tsb_arena_reserve(tsb_ctx* ctx, size_t bytes); /* pre-size from a plan's peak estimate */
+int tsb_arena_alloc(tsb_ctx* ctx, size_t bytes, void** ptr);
+int tsb_arena_release(tsb_ctx* ctx, void* ptr);
+int tsb_arena_trim(tsb_ctx* ctx); /* return all cached blocks to the driver */
+int tsb_arena_stats(tsb_ctx* ctx, tsb_arena_stats_t* stats);
+
+/* ---- single operations (the Box hooks) ---------------------------------------------------- */
+
+/* dst = transpose(src, perm): dst axis i is src axis perm[i] (numpy semantics). */
+int tsb_permute(tsb_ctx* ctx, const void* src, void* dst, int rank, const int32_t* extents,
+                const int32_t* perm, int elem_size, tsb_stream stream);
+
+/* dst[i_0..i_{out_rank-1}] = sum over dropped src ports of src[...], with dst port j attached
+ * to src port out_ports[j]; repeated ports tie dst axes to a diagonal (zero elsewhere). */
+int tsb_rewire(tsb_ctx* ctx, const void* src, int src_rank, const int32_t* src_extents,
+               int src_dtype, void* dst, int out_rank, const int32_t* out_ports, int dst_dtype,
+               int mode, tsb_stream stream);
+
+/* out[out_wires] = sum over wires not in out_wires of lhs[lhs_wires] * rhs[rhs_wires]
+ * (einsum with integer labels); out_wires may repeat or omit wires. */
+int tsb_contract2(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* lhs_wires,
+                  int lhs_dtype, const void* rhs, int rhs_rank, const int32_t* rhs_wires,
+                  int rhs_dtype, void* out, int out_rank, const int32_t* out_wires, int out_dtype,
+                  int n_wires, const int32_t* wire_extents, int mode, tsb_stream stream);
+
+/* dst = src[fixed] transposed: axis a of src is fixed to fixed_idx[a] (>= 0) or kept (-1);
+ * dst axis j is src axis out_axes[j] (the kept axes, in any order). */
+int tsb_slice(tsb_ctx* ctx, const void* src, int rank, const int32_t* extents,
+              const int32_t* fixed_idx, int out_rank, const int32_t* out_axes, void* dst,
+              int elem_size, tsb_stream stream);
+
+/* dst = stack(srcs, axis): n tensors of identical shape, new axis of extent n at `axis`. */
+int tsb_stack(tsb_ctx* ctx, const void* const* srcs, int n, int rank, const int32_t* extents,
+              int axis, void* dst, int elem_size, tsb_stream stream);
+
+/* out = a | b (TSB_SAT, 0/1 values) or a + b (TSB_COUNT), elementwise over n elements. */
+int tsb_union(tsb_ctx* ctx, const void* a, const void* b, void* out, int64_t n, int dtype,
+              int mode, tsb_stream stream);
+
+/* delta tensor: num_ports axes of extent dim, ones on the diagonal (num_ports = 0: scalar 1). */
+int tsb_spider(tsb_ctx* ctx, void* dst, int dim, int num_ports, int dtype, tsb_stream stream);
+int tsb_fill(tsb_ctx* ctx, void* dst, int64_t n, int64_t value, int dtype, tsb_stream stream);
+/* dst = (clamp ? src != 0 : src) converted to dst_dtype. */
+int tsb_convert(tsb_ctx* ctx, const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                int clamp, tsb_stream stream);
+
+/* result = 1 iff every one of the n elements equals 1.  Synchronises the stream. */
+int tsb_all_ones(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result,
+                 tsb_stream stream);
+/* Reads one element back as int64.  Synchronises the stream. */
+int tsb_scalar_to_host(tsb_ctx* ctx, const void* ptr, int dtype, int64_t* out, tsb_stream stream);
+
+/* ---- whole-tree plans --------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_leaves;
+  const int32_t* leaf_ranks;   /* [n_leaves] */
+  const int32_t* leaf_wires;   /* concatenated wire ids of every leaf, leaf order */
+  int32_t n_out;
+  const int32_t* out_wires;    /* wires of the result, in result-axis order (distinct) */
+  int32_t n_wires;
+  const int32_t* wire_extents; /* [n_wires] */
+  const int32_t* ssa_path;     /* [2 * (n_leaves - 1)] pairs; step s creates id n_leaves + s */
+  int32_t n_sliced;
+  const int32_t* sliced_wires; /* slice id digits, first wire most significant */
+  int32_t mode;                /* tsb_mode */
+  const uint8_t* wire_is_free; /* optional [n_wires]: 1 if summing the wire can multiply a count
+                                  (variables); 0 if it is functionally determined.  NULL = all 1 */
+  int32_t batch_log2;          /* tensors whose size incl. sliced wires is <= 2^batch_log2 are
+                                  computed once for all slices; < 0 selects the default */
+  uint32_t flags;              /* TSB_PLAN_* */
+} tsb_plan_desc;
+
+#define TSB_PLAN_NO_GRAPH 1u     /* launch kernels directly instead of replaying a CUDA graph */
+#define TSB_PLAN_FORCE_GENERIC 2u /* use only the generic kernel (parity reference on device) */
+#define TSB_PLAN_NO_GEMM 4u      /* never lower a step to the tcgen05 GEMM */
+
+typedef struct {
+  int64_t n_slices;
+  int64_t peak_bytes;         /* arena bytes needed by one execution */
+  int64_t out_numel;
+  int32_t out_dtype;          /* u8 for TSB_SAT, i64 for TSB_COUNT */
+  int32_t n_steps;
+  int32_t n_kernels_shared;   /* kernels run once per execution */
+  int32_t n_kernels_per_slice;
+  double alg_bytes_shared;    /* algorithmic bytes of the once-only part */
+  double alg_bytes_per_slice;
+  double alg_ops_shared;
+  double alg_ops_per_slice;
+  int32_t log2_max_tensor;    /* elements, largest intermediate of one slice */
+  int32_t may_overflow;       /* counting bound exceeds int64 */
+} tsb_plan_info_t;
+
+int tsb_plan_create(tsb_ctx* ctx, const tsb_plan_desc* desc, tsb_plan** plan);
+int tsb_plan_info(const tsb_plan* plan, tsb_plan_info_t* info);
+/* JSON description of the lowered device program (tests interpret it on the host). */
+int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* needed);
+/* Contracts slices [slice_begin, slice_end) and combines them (or / sum) into `out`
+ * (out_numel elements of out_dtype, C-order over out_wires).  leaf_ptrs[i] is the u8 0/1
+ * device tensor of leaf i in its own axis order. */
+int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice_begin,
+                     int64_t slice_end, void* out, tsb_stream stream);
+/* Per-kernel device times (ms) of the last execution with timing enabled; see tsb_plan_set_timing. */
+int tsb_plan_set_timing(tsb_plan* plan, int enabled);
+int tsb_plan_timing_json(tsb_plan* plan, char* buf, size_t cap, size_t* needed);
+int tsb_plan_destroy(tsb_plan* plan);
+
+/* ---- micro-benchmark / test hooks for the individual kernels ------------------------------ */
+/* C[b][m][n] = sum_k A[b][m][k] * B[b][n][k], u8 operands, tcgen05 kind::i8 with s32 TMEM
+ * accumulators.  out_dtype u8: clamp (acc != 0) when mode is TSB_SAT, else low byte;
+ * out_dtype i32: exact.  Extents are given as log2 (bits). */
+int tsb_gemm_u8(tsb_ctx* ctx, const void* A, const void* B, void* C, int b_bits, int m_bits,
+                int n_bits, int k_bits, int out_dtype, int mode, tsb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSB_H_ */

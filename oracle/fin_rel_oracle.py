@@ -176,7 +176,7 @@ def contract2(
         res = einsum2(lhs_t, lhs_wires, rhs_t, rhs_wires, einsum_out_wires)
         res = (rewire_array if ref_quirk_rewire else rewire_array_exact)(res, rewire_out_ports)
     if mode == "count":
-        return np.ascontiguousarray(res)
+        return np.array(res, order="C")
     return clamp(res, ref_quirk_mod256=ref_quirk_mod256)
 
 

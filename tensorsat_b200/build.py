@@ -1,0 +1,69 @@
+"""
+Builds ``libtsb.so`` (the C-ABI library, include/tsb.h) for sm_100a with nvcc, in-tree.
+
+    python -m tensorsat_b200.build            # build if sources are newer than the library
+    python -m tensorsat_b200.build --force
+
+nvcc cross-compiles without a GPU; the built library travels to the GPU box with the
+repository snapshot (it is git-ignored, not gpurun-ignored).
+"""
+
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libtsb.so")
+SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libtsb.so cannot be built")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def sources() -> list[str]:
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def all_deps() -> list[str]:
+    deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+    deps += glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "emu", "*.h"))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "tsb.h"))
+    return deps
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale(LIB, all_deps()):
+        return LIB
+    objs = []
+    for src in sources():
+        obj = src[:-3] + ".o"
+        if force or _stale(obj, all_deps()):
+            cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+                   "--expt-relaxed-constexpr", "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.run(cmd, check=True)
+        objs.append(obj)
+    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcuda"], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,458 @@
+// lower.h — host-side lowering of box operations to kernel launches.
+//
+// Everything here is index bookkeeping: which label sits on which address bit of which
+// operand, which kernel can serve a step, and how its descriptor is filled.
+#pragma once
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <set>
+
+#include "k_generic.cuh"
+#include "k_merge.cuh"
+#include "k_permute.cuh"
+
+namespace tsb {
+
+// ---------------------------------------------------------------------------------------------
+// Context: device, caching arena, launch accounting
+// ---------------------------------------------------------------------------------------------
+struct Arena {
+  std::multimap<size_t, void*> free_blocks;  // size -> ptr
+  std::map<void*, size_t> live;              // handed out
+  std::map<void*, size_t> owned;             // every block obtained from the driver
+  tsb_arena_stats_t st{};
+
+  static size_t round_up(size_t n) {
+    const size_t q = n < (size_t(1) << 20) ? 512 : (size_t(1) << 20);
+    return n == 0 ? q : (n + q - 1) / q * q;
+  }
+  void* alloc(size_t bytes) {
+    const size_t need = round_up(bytes);
+    auto it = free_blocks.lower_bound(need);
+    // reuse a cached block unless it would waste more than half of it
+    if (it != free_blocks.end() && it->first <= need * 2 + (size_t(1) << 20)) {
+      void* p = it->second;
+      live[p] = it->first;
+      st.in_use_bytes += it->first;
+      free_blocks.erase(it);
+      st.cache_hits++;
+      st.peak_in_use_bytes = std::max(st.peak_in_use_bytes, st.in_use_bytes);
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {
+      trim();
+      e = cudaMalloc(&p, need);
+    }
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("arena: cudaMalloc of %zu bytes failed: %s", need, cudaGetErrorString(e));
+      throw Error{TSB_ERR_OOM};
+    }
+    owned[p] = need;
+    live[p] = need;
+    st.reserved_bytes += need;
+    st.in_use_bytes += need;
+    st.device_allocs++;
+    st.peak_in_use_bytes = std::max(st.peak_in_use_bytes, st.in_use_bytes);
+    return p;
+  }
+  void release(void* p) {
+    auto it = live.find(p);
+    TSB_CHECK(it != live.end(), TSB_ERR_INVALID, "arena: release of a pointer the arena does not own");
+    st.in_use_bytes -= it->second;
+    free_blocks.emplace(it->second, p);
+    live.erase(it);
+  }
+  void trim() {
+    for (auto& kv : free_blocks) {
+      cudaFree(kv.second);
+      st.reserved_bytes -= kv.first;
+      owned.erase(kv.second);
+    }
+    free_blocks.clear();
+  }
+  ~Arena() {
+    for (auto& kv : owned) cudaFree(kv.first);
+  }
+};
+
+}  // namespace tsb
+
+struct tsb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  tsb::Arena arena;
+  int* d_flag = nullptr;  // scratch for all_ones
+  uint8_t* d_one = nullptr;  // the u8 scalar 1
+};
+
+namespace tsb {
+
+// RAII temp buffer from the arena (released on scope exit; safe for stream-ordered reuse)
+struct Temp {
+  tsb_ctx* ctx;
+  void* p = nullptr;
+  Temp(tsb_ctx* c, size_t bytes) : ctx(c) { p = c->arena.alloc(bytes); }
+  ~Temp() { if (p) ctx->arena.release(p); }
+  Temp(const Temp&) = delete;
+  Temp& operator=(const Temp&) = delete;
+};
+
+inline int grid_for(tsb_ctx* ctx, int64_t work_items, int threads, int per_sm = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Labelled dims: the common currency of the lowering.
+// ---------------------------------------------------------------------------------------------
+struct LDim {
+  int32_t label;
+  int64_t ext;
+  int64_t sl = 0, sr = 0, so = 0;  // element strides (0 = absent)
+  bool in_l = false, in_r = false, in_o = false;
+};
+
+// Builds the generic-kernel descriptor from labelled dims (free = in_o).  Free dims iterate in
+// decreasing output stride so that consecutive threads write consecutive addresses.
+inline GenDesc make_gen_desc(std::vector<LDim> dims, int dl, int dr, int dout, bool clamp,
+                             bool has_rhs, bool accumulate) {
+  std::vector<LDim> fr, rd;
+  for (auto& d : dims) {
+    if (d.ext == 1) continue;
+    (d.in_o ? fr : rd).push_back(d);
+  }
+  std::stable_sort(fr.begin(), fr.end(), [](const LDim& a, const LDim& b) { return a.so > b.so; });
+  std::stable_sort(rd.begin(), rd.end(), [](const LDim& a, const LDim& b) {
+    return a.sl != b.sl ? a.sl > b.sl : a.sr > b.sr;
+  });
+  auto merge = [](std::vector<LDim>& v) {
+    std::vector<LDim> o;
+    for (auto& d : v) {
+      if (!o.empty()) {
+        LDim& p = o.back();  // p is the outer dim, d the inner one
+        if (p.sl == d.sl * d.ext && p.sr == d.sr * d.ext && p.so == d.so * d.ext) {
+          p.ext *= d.ext;
+          p.sl = d.sl; p.sr = d.sr; p.so = d.so;
+          continue;
+        }
+      }
+      o.push_back(d);
+    }
+    v.swap(o);
+  };
+  merge(fr);
+  merge(rd);
+  TSB_CHECK((int)(fr.size() + rd.size()) <= kGenMaxDims, TSB_ERR_UNSUPPORTED,
+            "generic kernel: too many non-mergeable dimensions (%zu)", fr.size() + rd.size());
+  GenDesc g{};
+  g.n_free = (int)fr.size();
+  g.n_red = (int)rd.size();
+  g.n_out_iter = 1;
+  g.n_red_iter = 1;
+  int i = 0;
+  for (auto& d : fr) {
+    TSB_CHECK(d.ext <= INT32_MAX, TSB_ERR_UNSUPPORTED, "dimension too large");
+    g.ext[i] = (int32_t)d.ext; g.sl[i] = d.sl; g.sr[i] = d.sr; g.so[i] = d.so;
+    g.n_out_iter *= d.ext; i++;
+  }
+  for (auto& d : rd) {
+    TSB_CHECK(d.ext <= INT32_MAX, TSB_ERR_UNSUPPORTED, "dimension too large");
+    g.ext[i] = (int32_t)d.ext; g.sl[i] = d.sl; g.sr[i] = d.sr; g.so[i] = 0;
+    g.n_red_iter *= d.ext; i++;
+  }
+  g.dl = dl; g.dr = dr; g.dout = dout;
+  g.clamp = clamp; g.has_rhs = has_rhs; g.accumulate = accumulate;
+  return g;
+}
+
+inline void launch_generic(tsb_ctx* ctx, const GenDesc& g, const void* lhs, const void* rhs, void* out,
+                           cudaStream_t stream) {
+  const int grid = grid_for(ctx, g.n_out_iter, 256);
+  TSB_LAUNCH(k_generic, dim3(grid), dim3(256), 0, stream, g, lhs, rhs, out);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
+// Appends runs mapping input bit `in` -> output bit `out` (merging with the previous run).
+inline void runs_add(BitRuns& r, int in, int out) {
+  if (r.n > 0) {
+    const int k = r.n - 1;
+    if (r.in_shift[k] + r.len[k] == in && r.out_shift[k] + r.len[k] == out) {
+      r.len[k]++;
+      return;
+    }
+  }
+  TSB_CHECK(r.n < kMaxRuns, TSB_ERR_UNSUPPORTED, "index map needs more than %d bit runs", kMaxRuns);
+  r.in_shift[r.n] = (uint8_t)in;
+  r.len[r.n] = 1;
+  r.out_shift[r.n] = (uint8_t)out;
+  r.n++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bit-level tensors: a tensor with power-of-two extents is a list of bit labels, MSB first.
+// ---------------------------------------------------------------------------------------------
+using BitLabels = std::vector<int64_t>;  // label * 64 + bit-within-label, most significant first
+
+inline bool all_pow2(const int32_t* ext, int n) {
+  for (int i = 0; i < n; i++)
+    if (!is_pow2(ext[i])) return false;
+  return true;
+}
+
+// wires + extents (pow2) -> bit labels, MSB first
+inline BitLabels bit_labels(const int32_t* wires, int rank, const int32_t* wire_ext) {
+  BitLabels b;
+  for (int i = 0; i < rank; i++) {
+    const int nb = ilog2(wire_ext[wires[i]]);
+    for (int q = nb - 1; q >= 0; q--) b.push_back((int64_t)wires[i] * 64 + q);
+  }
+  return b;
+}
+
+inline std::map<int64_t, int> positions(const BitLabels& b) {
+  std::map<int64_t, int> p;
+  const int n = (int)b.size();
+  for (int i = 0; i < n; i++) p[b[i]] = n - 1 - i;  // address bit
+  return p;
+}
+
+inline bool has_dups(const BitLabels& b) {
+  std::set<int64_t> s(b.begin(), b.end());
+  return s.size() != b.size();
+}
+
+// ---- permutation lowering ---------------------------------------------------------------
+// src_bits / dst_bits: the same label set in two orders (MSB first); esz_log2 extra identical low bits.
+// Returns false if the fast kernel cannot serve it (caller falls back to the generic kernel).
+inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits, int esz_log2, PermDesc& d, int& G) {
+  const int r = (int)src_bits.size() + esz_log2;  // in byte-address bits
+  if (r < 9 || r > 62) return false;
+  // label at each byte-address bit of src/dst (element-size bits get pseudo labels -1-q)
+  std::vector<int64_t> s(r), t(r);
+  for (int q = 0; q < esz_log2; q++) s[q] = t[q] = -1 - q;
+  for (int i = 0; i < (int)src_bits.size(); i++) s[r - 1 - i] = src_bits[i];
+  for (int i = 0; i < (int)dst_bits.size(); i++) t[r - 1 - i] = dst_bits[i];
+  std::map<int64_t, int> spos, dpos;
+  for (int i = 0; i < r; i++) { spos[s[i]] = i; dpos[t[i]] = i; }
+  int g = 0;
+  while (g < 4 && g < r && s[g] == t[g]) g++;
+  G = 1 << g;
+  const int tb = std::min(r, 13);
+  const int a = std::min(7, r), b = std::min(7, r);
+  std::set<int64_t> T;
+  for (int i = 0; i < a; i++) T.insert(s[i]);
+  for (int i = 0; i < b; i++) T.insert(t[i]);
+  for (int i = 0; (int)T.size() < tb && i < r; i++) {
+    T.insert(t[i]);
+    if ((int)T.size() < tb) T.insert(s[i]);
+  }
+  const int tbits = (int)T.size();
+  if (tbits > kPermMaxTileBits) return false;
+  // tile-local bit index of each tile label in source order / destination order
+  std::vector<int64_t> ts, td;
+  for (int i = 0; i < r; i++) if (T.count(s[i])) ts.push_back(s[i]);
+  for (int i = 0; i < r; i++) if (T.count(t[i])) td.push_back(t[i]);
+  std::map<int64_t, int> tspos, tdpos;
+  for (int i = 0; i < tbits; i++) { tspos[ts[i]] = i; tdpos[td[i]] = i; }
+  d = PermDesc{};
+  d.g = g; d.tbits = tbits; d.a_bits = a; d.b_bits = b;
+  for (int i = a; i < tbits; i++) runs_add(d.src_hi, i - a, spos[ts[i]]);
+  for (int i = b; i < tbits; i++) runs_add(d.dst_hi, i - b, dpos[td[i]]);
+  for (int i = 0; i < tbits; i++) runs_add(d.d2s, i, tspos[td[i]]);
+  int ci = 0;
+  BitRuns cs{}, cd{};
+  // CTA index bits follow destination order so that neighbouring CTAs write neighbouring lines;
+  // the source-side map is generally not monotone, so its runs are added one bit at a time.
+  for (int i = 0; i < r; i++) {
+    if (T.count(t[i])) continue;
+    runs_add(cd, ci, i);
+    runs_add(cs, ci, spos[t[i]]);
+    ci++;
+  }
+  d.cta_src = cs; d.cta_dst = cd;
+  d.n_tiles = int64_t(1) << (r - tbits);
+  return true;
+}
+
+inline size_t perm_smem_bytes(const PermDesc& d) {
+  return (size_t(1) << d.tbits) + 8 * (size_t(1) << (d.tbits - d.a_bits)) + 8 * (size_t(1) << (d.tbits - d.b_bits)) +
+         2 * (size_t(1) << (d.tbits - 4)) + 16;
+}
+
+inline void launch_permute_fast(tsb_ctx* ctx, const PermDesc& d, int G, const void* src, void* dst, cudaStream_t stream) {
+  const size_t smem = perm_smem_bytes(d);
+  const int grid = (int)std::min<int64_t>(d.n_tiles, (int64_t)ctx->sm_count * 8);
+  const uint8_t* s = (const uint8_t*)src;
+  uint8_t* t = (uint8_t*)dst;
+  switch (G) {
+    case 1: TSB_LAUNCH(k_permute<1>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
+    case 2: TSB_LAUNCH(k_permute<2>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
+    case 4: TSB_LAUNCH(k_permute<4>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
+    case 8: TSB_LAUNCH(k_permute<8>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
+    default: TSB_LAUNCH(k_permute<16>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
+  }
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
+// General bit-permutation (or gather with holes): dst[dst_bits] = src[src_bits], where every dst label
+// must occur in src_pos (label -> source ELEMENT address bit).  Chooses fast kernel / memcpy / generic.
+inline void permute_bits(tsb_ctx* ctx, const void* src, const BitLabels& src_bits, void* dst,
+                         const BitLabels& dst_bits, int elem_size, cudaStream_t stream) {
+  TSB_CHECK(src_bits.size() == dst_bits.size(), TSB_ERR_INVALID, "permute: rank mismatch");
+  const int n = (int)src_bits.size();
+  if (src_bits == dst_bits) {
+    if (src != dst)
+      TSB_CUDA(cudaMemcpyAsync(dst, src, (size_t)elem_size << n, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  PermDesc pd;
+  int G = 1;
+  if (aligned && !has_dups(src_bits) && make_perm_desc(src_bits, dst_bits, ilog2(elem_size), pd, G)) {
+    launch_permute_fast(ctx, pd, G, src, dst, stream);
+    return;
+  }
+  auto sp = positions(src_bits);
+  std::vector<LDim> dims;
+  for (int i = 0; i < n; i++) {
+    LDim d{};
+    d.label = i; d.ext = 2; d.in_l = d.in_o = true;
+    d.so = int64_t(1) << (n - 1 - i);
+    d.sl = int64_t(1) << sp.at(dst_bits[i]);
+    dims.push_back(d);
+  }
+  const int dt = elem_size == 1 ? TSB_U8 : elem_size == 4 ? TSB_I32 : TSB_I64;
+  TSB_CHECK(elem_size == 1 || elem_size == 4 || elem_size == 8, TSB_ERR_UNSUPPORTED, "element size %d", elem_size);
+  GenDesc g = make_gen_desc(dims, dt, dt, dt, false, false, false);
+  launch_generic(ctx, g, src, nullptr, dst, stream);
+}
+
+// ---- merge lowering -------------------------------------------------------------------------
+struct MergeArgs {
+  MergeDesc d;
+  bool ok = false;
+};
+
+// lhs_bits / rhs_bits / out_bits: bit labels MSB first.  Labels of lhs/rhs not in out are summed.
+// Returns ok=false if the monotone-merge preconditions do not hold.
+inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs_bits, const BitLabels& out_bits,
+                                 bool accumulate) {
+  MergeArgs m;
+  const int R = (int)out_bits.size();
+  if (R < 4 || R > 62) return m;
+  if (has_dups(lhs_bits) || has_dups(out_bits) || (rhs_bits && has_dups(*rhs_bits))) return m;
+  auto lp = positions(lhs_bits);
+  std::map<int64_t, int> rp;
+  if (rhs_bits) rp = positions(*rhs_bits);
+  auto op = positions(out_bits);
+  // every out label must come from an operand
+  for (auto& kv : op)
+    if (!lp.count(kv.first) && !rp.count(kv.first)) return m;
+  // monotone: operand positions strictly increase with out position
+  auto monotone = [&](const std::map<int64_t, int>& pp, int& nib, int& nlow) {
+    int last = -1;
+    nib = 0; nlow = 0;
+    for (int j = 0; j < R; j++) {
+      const int64_t lab = out_bits[R - 1 - j];
+      auto it = pp.find(lab);
+      if (it == pp.end()) continue;
+      if (it->second <= last) return false;
+      last = it->second;
+      if (j < 4) {
+        if (it->second != nlow) return false;  // must be the operand's lowest address bits
+        nib |= 1 << j;
+        nlow++;
+      }
+    }
+    return true;
+  };
+  int nibL = 0, nibR = 0, nl = 0, nr = 0;
+  if (!monotone(lp, nibL, nl)) return m;
+  if (rhs_bits && !monotone(rp, nibR, nr)) return m;
+  MergeDesc& d = m.d;
+  d = MergeDesc{};
+  d.R = R;
+  d.nibL = nibL; d.nibR = nibR;
+  d.has_rhs = rhs_bits ? 1 : 0;
+  d.accumulate = accumulate ? 1 : 0;
+  const int vb = R - 4;
+  d.tile_bits = std::min(vb, std::min(kMergeTileBits, std::max(7, R - 14)));
+  d.n_vec = int64_t(1) << vb;
+  for (int j = 4; j < R; j++) {
+    const int64_t lab = out_bits[R - 1 - j];
+    const bool lo = (j - 4) < d.tile_bits;
+    const int in = lo ? j - 4 : j - 4 - d.tile_bits;
+    auto il = lp.find(lab);
+    if (il != lp.end()) runs_add(lo ? d.loL : d.hiL, in, il->second);
+    auto ir = rp.find(lab);
+    if (ir != rp.end()) runs_add(lo ? d.loR : d.hiR, in, ir->second);
+  }
+  // summed labels: everything in lhs/rhs that is not in out (lone labels get stride 0 on the other side)
+  std::vector<int64_t> ks;
+  for (auto& kv : lp) if (!op.count(kv.first)) ks.push_back(kv.first);
+  for (auto& kv : rp) if (!op.count(kv.first) && !lp.count(kv.first)) ks.push_back(kv.first);
+  if ((int)ks.size() > kMergeMaxK) return m;
+  // iterate the lowest-address summed label fastest
+  std::sort(ks.begin(), ks.end(), [&](int64_t a, int64_t b) {
+    const int pa = lp.count(a) ? lp[a] : 64 + rp[a], pb = lp.count(b) ? lp[b] : 64 + rp[b];
+    return pa < pb;
+  });
+  d.kbits = (int)ks.size();
+  for (int q = 0; q < d.kbits; q++) {
+    d.ksL[q] = lp.count(ks[q]) ? int64_t(1) << lp[ks[q]] : 0;
+    d.ksR[q] = rp.count(ks[q]) ? int64_t(1) << rp[ks[q]] : 0;
+  }
+  m.ok = true;
+  return m;
+}
+
+template <typename TL, typename TR, typename TO>
+inline void launch_merge_t(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, bool clamp,
+                           cudaStream_t stream) {
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 16);
+  auto kc = k_merge<TL, TR, TO, 1>;
+  auto kn = k_merge<TL, TR, TO, 0>;
+  if (clamp)
+    TSB_LAUNCH(kc, dim3(grid), dim3(kMergeThreads), 0, stream, d, (const TL*)l, (const TR*)r, (TO*)o);
+  else
+    TSB_LAUNCH(kn, dim3(grid), dim3(kMergeThreads), 0, stream, d, (const TL*)l, (const TR*)r, (TO*)o);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
+template <typename TL, typename TR>
+inline void launch_merge_o(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, int dout,
+                           bool clamp, cudaStream_t s) {
+  if (dout == TSB_U8) launch_merge_t<TL, TR, uint8_t>(ctx, d, l, r, o, clamp, s);
+  else if (dout == TSB_I32) launch_merge_t<TL, TR, int32_t>(ctx, d, l, r, o, clamp, s);
+  else launch_merge_t<TL, TR, int64_t>(ctx, d, l, r, o, clamp, s);
+}
+
+template <typename TL>
+inline void launch_merge_r(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, int dr, int dout,
+                           bool clamp, cudaStream_t s) {
+  if (dr == TSB_U8) launch_merge_o<TL, uint8_t>(ctx, d, l, r, o, dout, clamp, s);
+  else if (dr == TSB_I32) launch_merge_o<TL, int32_t>(ctx, d, l, r, o, dout, clamp, s);
+  else launch_merge_o<TL, int64_t>(ctx, d, l, r, o, dout, clamp, s);
+}
+
+inline void launch_merge(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
+                         int dout, bool clamp, cudaStream_t s) {
+  if (!d.has_rhs) dr = TSB_U8;
+  if (dl == TSB_U8) launch_merge_r<uint8_t>(ctx, d, l, r, o, dr, dout, clamp, s);
+  else if (dl == TSB_I32) launch_merge_r<int32_t>(ctx, d, l, r, o, dr, dout, clamp, s);
+  else launch_merge_r<int64_t>(ctx, d, l, r, o, dr, dout, clamp, s);
+}
+
+}  // namespace tsb

@@ -102,7 +102,7 @@ class _CudaTensorBox(TensorLikeBox):
                 return cls.from_device(tensor)
         except ModuleNotFoundError:  # pragma: no cover
             pass
-        arr = np.ascontiguousarray(np.asarray(tensor))
+        arr = np.array(tensor, order="C")  # (ascontiguousarray would promote rank 0 to rank 1)
         if cls._MODE == MODE_SAT:
             if arr.dtype != np.uint8:
                 raise TypeError("Boolean tensors must have dtype uint8.")
@@ -284,7 +284,7 @@ class _CudaTensorBox(TensorLikeBox):
             )
             if new._dev is None:
                 new._axes = None
-                new._host = np.ascontiguousarray(new._host)
+                new._host = np.array(new._host, order="C")
                 new._host.setflags(write=False)
             return new
         dev, pdims, axes = self._physical()
@@ -410,7 +410,7 @@ class _CudaTensorBox(TensorLikeBox):
 
     def __hash__(self) -> int:
         if self._hash_cache is None:
-            self._hash_cache = hash((self._dims, np.ascontiguousarray(self.tensor).tobytes()))
+            self._hash_cache = hash((self._dims, np.array(self.tensor, order="C").tobytes()))
         return self._hash_cache
 
 

@@ -1,0 +1,40 @@
+"""
+TEST INFRASTRUCTURE: builds ``tests/emu/_build/libtsb_emu.so`` — the same sources as libtsb.so
+compiled by g++ with ``-DTSB_HOST_EMU`` against the host emulation of the CUDA execution model
+in ``tensorsat_b200/csrc/emu/cuda_emu.h``.  It lets the CPU test-suite run the SIMT kernels and
+the whole lowering / plan executor without a GPU.  The product never loads this library.
+"""
+
+from __future__ import annotations
+
+import glob
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "tensorsat_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libtsb_emu.so")
+SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu"]
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(OUT, exist_ok=True)
+    deps = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(CSRC, "emu", "*"))
+    deps.append(os.path.join(ROOT, "include", "tsb.h"))
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps if os.path.isfile(d)):
+        return LIB
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(OUT, s[:-3] + ".o")
+        subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-DTSB_HOST_EMU", "-x", "c++", "-c",
+                        os.path.join(CSRC, s), "-o", obj, "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
+                        "-Wno-sign-compare"], check=True)
+        objs.append(obj)
+    subprocess.run(["g++", "-shared", "-o", LIB, *objs], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

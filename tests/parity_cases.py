@@ -1,0 +1,368 @@
+"""
+Parity cases shared by the CPU suite (C-ABI code running on the host emulation, tests/emu) and
+the GPU suite (the real libtsb.so on a B200).  Every case calls the product through its public
+box / contraction API (hence through the C-ABI) and compares bit-for-bit with the oracle.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import fin_rel_oracle as O
+from tensorsat_b200.contractions.simple import SimpleContraction
+from tensorsat_b200.contractions.tree import TreeContraction
+from tensorsat_b200.diagrams import FinSet
+from tensorsat_b200.lang.fin_rel import CudaCountRel, CudaFinRel
+from tensorsat_b200.lib import bincirc as bc
+from tensorsat_b200.lib.sat import CNFInstance
+from tensorsat_b200.planner import ContractionTree, Network
+from tensorsat_b200.planner.search import find_tree_elimination
+
+from tests.conftest import load_golden
+
+SCALE = {"big_bits": 15}  # raised by the GPU suite
+
+
+def _arr(x, shape=None, dtype=np.uint8):
+    a = np.array(x, dtype=dtype)
+    return a.reshape(shape) if shape is not None else a
+
+
+def _rand01(rng, shape, p=0.5):
+    return (rng.random(shape) < p).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------ golden ops
+def test_contract2_golden():
+    """FinRel.contract2 outputs recorded from the reference (where it is well defined)."""
+    n = 0
+    for c in load_golden("ops.json"):
+        if c["op"] != "contract2":
+            continue
+        lhs, rhs = _arr(c["lhs"], c["lhs_shape"]), _arr(c["rhs"], c["rhs_shape"])
+        ow = c["out_wires"]
+        got = CudaFinRel.contract2(CudaFinRel(lhs), c["lhs_wires"], CudaFinRel(rhs), c["rhs_wires"], ow)
+        ow_eff = ow if ow is not None else sorted(set(c["lhs_wires"]).symmetric_difference(c["rhs_wires"]))
+        want = O.contract2(lhs, c["lhs_wires"], rhs, c["rhs_wires"], ow_eff)
+        assert got.tensor.dtype == np.uint8
+        assert got.tensor.shape == want.shape
+        assert np.array_equal(got.tensor, want), c
+        n += 1
+        # counting semiring on the same case
+        gotc = CudaCountRel.contract2(CudaCountRel(lhs), c["lhs_wires"], CudaCountRel(rhs), c["rhs_wires"], ow)
+        wantc = O.contract2(lhs, c["lhs_wires"], rhs, c["rhs_wires"], ow_eff, mode="count")
+        assert gotc.tensor.dtype == np.int64 and np.array_equal(gotc.tensor, wantc)
+    assert n >= 50
+
+
+def test_rewire_golden():
+    for c in load_golden("ops.json"):
+        if c["op"] != "rewire":
+            continue
+        t = _arr(c["tensor"], c["shape"])
+        got = CudaFinRel(t).rewire(c["ports"])
+        want = O.rewire(t, c["ports"])
+        assert got.tensor.shape == want.shape and np.array_equal(got.tensor, want), c
+        gotc = CudaCountRel(t).rewire(c["ports"])
+        assert np.array_equal(gotc.tensor, O.rewire(t, c["ports"], mode="count"))
+
+
+def test_small_ops_golden():
+    for c in load_golden("ops.json"):
+        if c["op"] == "spider":
+            got = CudaFinRel.spider(FinSet(c["size"]), c["num_ports"])
+            assert np.array_equal(got.tensor, _arr(c["res"]))
+        elif c["op"] == "scalar":
+            got = CudaFinRel.scalar(c["value"])
+            assert got.shape == () and bool(got) == c["bool"]
+            assert np.array_equal(got.tensor, _arr(c["res"]))
+        elif c["op"] == "slice_union_stack":
+            a, b = CudaFinRel(_arr(c["a"], c["shape"])), CudaFinRel(_arr(c["b"], c["shape"]))
+            idx = tuple(slice(None) if i is None else i for i in c["idx"])
+            assert np.array_equal(a[idx].tensor, _arr(c["getitem"], c["getitem_shape"]))
+            assert np.array_equal((a + b).tensor, _arr(c["union"]))
+            assert np.array_equal(CudaFinRel.stack([a, b, a], c["port"]).tensor, _arr(c["stack"]))
+        elif c["op"] == "einsum":
+            from tensorsat_b200 import autoray_backend as ab
+
+            got = ab.einsum(c["eq"], CudaFinRel(_arr(c["lhs"])), CudaFinRel(_arr(c["rhs"])))
+            assert np.array_equal(got.tensor, _arr(c["res"]))
+        elif c["op"] == "transpose":
+            from tensorsat_b200 import autoray_backend as ab
+
+            got = ab.transpose(CudaFinRel(_arr(c["tensor"])), c["perm"])
+            assert np.array_equal(got.tensor, _arr(c["res"]))
+
+
+def test_mod256_quirk_documented():
+    """The product implements count > 0; the reference's np.sign(dtype=uint8) says 0 for 256 witnesses."""
+    ones8 = CudaFinRel(np.ones((2,) * 8, dtype=np.uint8))
+    w = list(range(8))
+    assert bool(CudaFinRel.contract2(ones8, w, ones8, w, [])) is True
+    assert int(CudaCountRel.contract2(CudaCountRel.from_rel(ones8), w, CudaCountRel.from_rel(ones8), w, [])) == 256
+    q = [c for c in load_golden("ops.json") if c["op"] == "contract2_quirk" and c["k"] == 8][0]
+    assert q["res"] == 0
+    assert int(O.contract2(np.ones((2,) * 8, np.uint8), w, np.ones((2,) * 8, np.uint8), w, [], ref_quirk_mod256=True)) == 0
+
+
+# ------------------------------------------------------------------------------------ random contract2
+def _random_contract_case(rng, nl, nr, n_shared, n_out_drop, dims=(2,)):
+    n_wires = nl + nr - n_shared
+    wires = list(rng.permutation(n_wires))
+    shared = wires[:n_shared]
+    lw = shared + wires[n_shared : n_shared + (nl - n_shared)]
+    rw = shared + wires[nl:]
+    lw = [int(w) for w in rng.permutation(lw)]
+    rw = [int(w) for w in rng.permutation(rw)]
+    allw = sorted(set(lw) | set(rw))
+    drop = set(int(w) for w in rng.choice(allw, size=min(n_out_drop, len(allw)), replace=False)) if n_out_drop else set()
+    ow = [int(w) for w in rng.permutation([w for w in allw if w not in drop])]
+    wdim = {w: int(rng.choice(dims)) for w in allw}
+    return lw, rw, ow, wdim
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_contract2_random_medium(seed):
+    """Ranks large enough for the merge / permute kernels, arbitrary axis orders."""
+    rng = np.random.default_rng(1000 + seed)
+    nl, nr = int(rng.integers(6, 13)), int(rng.integers(6, 13))
+    ns = int(rng.integers(1, min(nl, nr)))
+    lw, rw, ow, wdim = _random_contract_case(rng, nl, nr, ns, int(rng.integers(0, 5)))
+    lhs = _rand01(rng, [wdim[w] for w in lw], 0.3)
+    rhs = _rand01(rng, [wdim[w] for w in rw], 0.3)
+    got = CudaFinRel.contract2(CudaFinRel(lhs), lw, CudaFinRel(rhs), rw, ow)
+    assert np.array_equal(got.tensor, O.contract2(lhs, lw, rhs, rw, ow))
+    gotc = CudaCountRel.contract2(CudaCountRel(lhs), lw, CudaCountRel(rhs), rw, ow)
+    assert np.array_equal(gotc.tensor, O.contract2(lhs, lw, rhs, rw, ow, mode="count"))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_contract2_random_mixed_dims(seed):
+    rng = np.random.default_rng(2000 + seed)
+    lw, rw, ow, wdim = _random_contract_case(rng, 5, 5, 2, 2, dims=(2, 3, 4))
+    lhs = _rand01(rng, [wdim[w] for w in lw])
+    rhs = _rand01(rng, [wdim[w] for w in rw])
+    got = CudaFinRel.contract2(CudaFinRel(lhs), lw, CudaFinRel(rhs), rw, ow)
+    assert np.array_equal(got.tensor, O.contract2(lhs, lw, rhs, rw, ow))
+
+
+def test_contract2_ordered_big():
+    """An 'absorb' step in plan order (no permutes): big x small with batch wires, k = 1."""
+    rng = np.random.default_rng(7)
+    nb = SCALE["big_bits"]
+    big_w = list(range(nb + 1))          # wire 0 is summed, the rest kept
+    small_w = [0, 3, 5, nb + 1, nb + 2]  # shares 0 (summed), 3, 5 (batch), adds two wires
+    ow = sorted(set(big_w[1:]) | set(small_w[1:]))
+    big = _rand01(rng, (2,) * len(big_w), 0.4)
+    small = _rand01(rng, (2,) * len(small_w), 0.6)
+    got = CudaFinRel.contract2(CudaFinRel(big), big_w, CudaFinRel(small), small_w, ow)
+    want = O.contract2(big, big_w, small, small_w, ow)
+    assert np.array_equal(got.tensor, want)
+    gotc = CudaCountRel.contract2(CudaCountRel(big), big_w, CudaCountRel(small), small_w, ow)
+    assert np.array_equal(gotc.tensor, O.contract2(big, big_w, small, small_w, ow, mode="count"))
+
+
+def test_contract2_validation_errors():
+    a, b = CudaFinRel(np.ones((2, 2), np.uint8)), CudaFinRel(np.ones((2,), np.uint8))
+    with pytest.raises(ValueError):
+        CudaFinRel.contract2(a, [0], b, [1])  # wrong number of lhs wires
+    with pytest.raises(ValueError):
+        CudaFinRel.contract2(a, [0, 1], b, [1], [2])  # output wire from nowhere
+    with pytest.raises(TypeError):
+        CudaFinRel.contract2(a, [0, 1], CudaCountRel(np.ones((2,), np.int64)), [1])
+    with pytest.raises(ValueError):
+        CudaFinRel(np.full((2,), 2, np.uint8))
+    with pytest.raises(ValueError):
+        bool(a)
+    with pytest.raises(NotImplementedError):
+        a[(slice(0, 1), 0)]
+    with pytest.raises(ValueError):
+        a.rewire([2])
+
+
+# ------------------------------------------------------------------------------------ permutes
+@pytest.mark.parametrize("seed", range(8))
+def test_permute_random(seed):
+    rng = np.random.default_rng(3000 + seed)
+    r = int(rng.integers(9, SCALE["big_bits"] + 1))
+    t = _rand01(rng, (2,) * r)
+    perm = [int(p) for p in rng.permutation(r)]
+    box = CudaFinRel(t).rewire(perm)
+    assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm))
+
+
+def test_permute_keeps_low_axes_and_wide_elements():
+    rng = np.random.default_rng(5)
+    r = 13
+    t = rng.integers(0, 1 << 40, size=(2,) * r, dtype=np.int64)
+    for perm in ([1, 0] + list(range(2, r)), list(range(r - 3, -1, -1)) + [r - 2, r - 1], list(range(r))[::-1]):
+        box = CudaCountRel(t).rewire(perm)
+        assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm))
+    u = _rand01(rng, (2,) * 14)
+    for keep in (1, 2, 3, 4, 5):  # low axes left in place: gather groups of 2..16 bytes
+        perm = [int(p) for p in rng.permutation(14 - keep)] + list(range(14 - keep, 14))
+        box = CudaFinRel(u).rewire(perm)
+        assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(u, perm))
+
+
+# ------------------------------------------------------------------------------------ whole networks
+def _network_and_leaves(diagram):
+    flat = diagram.flatten()
+    return flat, Network.from_diagram(flat)
+
+
+def _oracle_tree(flat, tree, mode="sat"):
+    leaves = [b.tensor for b in flat.boxes]
+    return O.execute_tree(tree.network.inputs, tree.network.output, leaves, tree.ssa_path,
+                          tree.sliced_wires, mode=mode, size_dict=tree.network.size_dict)
+
+
+def test_kissat_verdicts():
+    """examples/test_sat_solver.py:22-190 through the DIMACS parser and the plan executor."""
+    import os
+
+    from tests.conftest import GOLDEN
+
+    g = load_golden("networks.json")["kissat"]
+    checked = 0
+    for rec in g:
+        if rec["log2_max_size"] > SCALE["big_bits"] + 3:
+            continue
+        with open(os.path.join(GOLDEN, "kissat", rec["name"] + ".cnf")) as f:
+            cnf = CNFInstance.from_dimacs(f.read())
+        diagram = (cnf.inputs(None) >> cnf.diagram()).flatten()
+        contraction = TreeContraction(CudaFinRel, diagram.wiring, ssa_path=rec.get("ssa_path"), trials=2)
+        assert bool(contraction.contract(diagram)) == rec["expected"], rec["name"]
+        checked += 1
+    assert checked >= 39
+
+
+def test_random_ksat_solution_tensors_and_counts():
+    for rec in load_golden("networks.json")["random"]:
+        cnf = CNFInstance.random(rec["k"], rec["n"], rec["m"], rng=rec["seed"])
+        diagram = cnf.diagram().flatten()
+        tc = TreeContraction(CudaFinRel, diagram.wiring, ssa_path=rec["ssa_path"])
+        sol = tc.contract(diagram)
+        got = sorted("".join(map(str, p)) for p in sol.to_set())
+        assert got == rec["solutions"]
+        brute = O.cnf_brute_force(cnf.num_vars, cnf.clauses).reshape((2,) * cnf.num_vars)
+        assert np.array_equal(sol.tensor, brute)
+        # decisions with partial inputs (the reference's assignment search, 02-random-ksat.ipynb:707-722)
+        for dec in rec["decisions"]:
+            dd = (cnf.inputs(dec["inputs"]) >> cnf.diagram()).flatten()
+            c2 = TreeContraction(CudaFinRel, dd.wiring, ssa_path=dec["ssa_path"])
+            assert bool(c2.contract(dd)) == dec["sat"]
+        # #SAT: same network, counting semiring, all inputs unknown
+        dd = (cnf.inputs(None) >> cnf.diagram()).flatten()
+        cc = TreeContraction(CudaCountRel, dd.wiring, trials=2, wire_is_free=[w < cnf.num_vars for w in dd.wiring.wires])
+        assert int(cc.contract(dd)) == len(rec["solutions"]) == int(brute.sum())
+
+
+def test_circuits_truth_tables():
+    diagrams = {"half_adder": bc.half_adder, "full_adder": bc.full_adder, "rc_adder(2)": bc.rc_adder(2),
+                "wallace_multiplier(2)": bc.wallace_multiplier(2), "wallace_multiplier(3)": bc.wallace_multiplier(3)}
+    for rec in load_golden("networks.json")["circuits"]:
+        d = diagrams[rec["name"]].flatten()
+        res = TreeContraction(CudaFinRel, d.wiring, ssa_path=rec["ssa_path"]).contract(d)
+        assert sorted("".join(map(str, p)) for p in res.to_set()) == rec["points"]
+    # multiplier semantics: a * b == p on every row
+    d = bc.wallace_multiplier(3).flatten()
+    res = TreeContraction(CudaFinRel, d.wiring, trials=2).contract(d)
+    for pt in res.to_set():
+        a = sum(b << i for i, b in enumerate(pt[0:3]))
+        b_ = sum(b << i for i, b in enumerate(pt[3:6]))
+        p = sum(b << i for i, b in enumerate(pt[6:]))
+        assert a * b_ == p
+
+
+def test_simple_contraction_matches_reference():
+    for rec in load_golden("networks.json")["simple"]:
+        if "name" in rec:
+            d = bc.full_adder
+            res = SimpleContraction(CudaFinRel, d.wiring, rec["linear_path"]).contract(d)
+            assert sorted("".join(map(str, p)) for p in res.to_set()) == rec["points"]
+        else:
+            cnf = CNFInstance.random(rec["k"], rec["n"], rec["m"], rng=rec["seed"])
+            d = cnf.diagram().flatten()
+            res = SimpleContraction(CudaFinRel, d.wiring, rec["linear_path"]).contract(d)
+            assert sorted("".join(map(str, p)) for p in res.to_set()) == rec["solutions"]
+
+
+@pytest.mark.parametrize("n,m,seed,target", [(14, 58, 3, 7), (16, 66, 1, 8), (12, 50, 4, 5)])
+def test_sliced_matches_unsliced_and_oracle(n, m, seed, target):
+    cnf = CNFInstance.random(3, n, m, rng=seed)
+    diagram = (cnf.inputs(None) >> cnf.diagram()).flatten()
+    flat, net = _network_and_leaves(diagram)
+    tree = find_tree_elimination(net, trials=4, seed=seed)
+    sliced = tree.slice_to(target)
+    assert sliced.num_slices > 1
+    brute = O.cnf_brute_force(n, cnf.clauses)
+    for box_class, mode in ((CudaFinRel, "sat"), (CudaCountRel, "count")):
+        free = [w < n for w in flat.wiring.wires]
+        full = TreeContraction(box_class, flat.wiring, tree=tree, wire_is_free=free).contract(flat)
+        part = TreeContraction(box_class, flat.wiring, tree=sliced, wire_is_free=free, batch_log2=4).contract(flat)
+        lazy = TreeContraction(box_class, flat.wiring, tree=sliced, wire_is_free=free).contract(flat)
+        want = _oracle_tree(flat, sliced, mode)
+        assert np.array_equal(full.tensor, want) and np.array_equal(part.tensor, want) and np.array_equal(lazy.tensor, want)
+        if mode == "count":
+            assert int(full) == int(brute.sum())
+        else:
+            assert bool(full) == bool(brute.any())
+
+
+def test_sliced_output_wires_are_stacked():
+    """Sliced wires that are output wires: per-slice results are stacked (Box.stack, diagrams.py:883-896)."""
+    cnf = CNFInstance.random(3, 8, 20, rng=2)
+    diagram = cnf.diagram().flatten()
+    flat, net = _network_and_leaves(diagram)
+    tree = find_tree_elimination(net, trials=2, seed=0)
+    want = O.cnf_brute_force(8, cnf.clauses).reshape((2,) * 8)
+    for sl in ((2,), (5, 0), (1, 7, 3)):
+        t = tree.with_sliced(sl)
+        got = TreeContraction(CudaFinRel, flat.wiring, tree=t, batch_log2=3).contract(flat)
+        assert np.array_equal(got.tensor, want)
+        gotc = TreeContraction(CudaCountRel, flat.wiring, tree=t, batch_log2=3,
+                               wire_is_free=[w < 8 for w in flat.wiring.wires]).contract(flat)
+        assert np.array_equal(gotc.tensor, want.astype(np.int64))
+        with pytest.raises(OverflowError):  # 74 summed wires, none declared as determined
+            TreeContraction(CudaCountRel, flat.wiring, tree=t).contract(flat)
+
+
+def test_generic_and_fast_plans_agree():
+    cnf = CNFInstance.random(3, 18, 60, rng=9)
+    diagram = (cnf.inputs("0?1" + "?" * 15) >> cnf.diagram()).flatten()
+    flat, net = _network_and_leaves(diagram)
+    tree = find_tree_elimination(net, trials=2, seed=1)
+    free = [w < 18 for w in flat.wiring.wires]
+    a = TreeContraction(CudaCountRel, flat.wiring, tree=tree, wire_is_free=free).contract(flat)
+    b = TreeContraction(CudaCountRel, flat.wiring, tree=tree, wire_is_free=free, force_generic=True).contract(flat)
+    assert int(a) == int(b) == int(_oracle_tree(flat, tree, "count"))
+
+
+def test_plan_reuse_with_changed_leaves():
+    """One contraction object, many input assignments (notebooks/01-introduction.ipynb:1824-1849)."""
+    cnf = CNFInstance.random(3, 3, 6, rng=3)  # golden G5
+    wiring = cnf.contraction_wiring()
+    contraction = TreeContraction(CudaFinRel, wiring, trials=2)
+    trace = {}
+    for spec in ("0??", "00?", "01?", "010", "011", "1??", "111"):
+        d = (cnf.inputs(spec) >> cnf.diagram()).flatten()
+        trace[spec] = bool(contraction.contract(d))
+    assert trace == {"0??": True, "00?": False, "01?": True, "010": False, "011": True, "1??": True, "111": True}
+
+
+def test_arena_is_reused_across_executions():
+    from tensorsat_b200 import _native
+
+    cnf = CNFInstance.random(3, 12, 50, rng=4)
+    d = (cnf.inputs(None) >> cnf.diagram()).flatten()
+    c = TreeContraction(CudaFinRel, d.wiring, trials=2)
+    c.contract(d)
+    before = _native.arena_stats()
+    for _ in range(3):
+        c.contract(d)
+    after = _native.arena_stats()
+    assert after["device_allocs"] == before["device_allocs"]
+    assert after["cache_hits"] >= before["cache_hits"] + 3
+    assert after["in_use_bytes"] == before["in_use_bytes"]

@@ -1,0 +1,150 @@
+"""Host-side logic: instance generators, DIMACS parser, diagram mirror, planner, slice partition."""
+
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tensorsat_b200.lib import bincirc as bc
+from tensorsat_b200.lib.sat import CNFInstance
+from tensorsat_b200.planner import ContractionTree, Network, find_tree, linear_to_ssa, ssa_to_linear
+from tensorsat_b200.planner.search import find_tree_elimination
+from tests.conftest import GOLDEN, load_golden
+
+
+def _digest(wiring):
+    blob = json.dumps([list(map(list, wiring.slot_wires_list)), list(wiring.out_wires)]).encode()
+    return hashlib.sha256(blob).hexdigest()
+
+
+def test_random_instances_match_reference_generator():
+    """CNFInstance.random RNG stream + bintree wiring (tensorsat/lib/sat.py:43-78,248-262)."""
+    assert CNFInstance.random(3, 4, 4, rng=0).clauses == ((2, 3, 4), (-4, -3, -1), (-3, -2, 4), (-4, -3, 1))  # G1
+    assert CNFInstance.random(3, 3, 6, rng=3).clauses == (
+        (-3, -1, 2), (-3, 1, 2), (1, 2, 3), (-2, -1, 3), (-1, 2, 3), (-2, 1, 3))  # G2
+    for rec in load_golden("instances.json")["random"]:
+        c = CNFInstance.random(rec["k"], rec["n"], rec["m"], rng=rec["seed"])
+        assert hashlib.sha256(json.dumps(c.clauses).encode()).hexdigest() == rec["clauses_sha256"]
+        if rec["n"] > 50:
+            continue
+        d = (c.inputs(None) >> c.diagram()).flatten()
+        assert d.wiring.num_wires == rec["num_wires"] and len(d.blocks) == rec["num_blocks"]
+        assert _digest(d.wiring) == rec["wiring_sha256"]
+        assert len(c.diagram().blocks) == rec["diagram_num_blocks"]
+        if rec["n"] <= 20:
+            assert _digest(c.contraction_wiring()) == rec["contraction_wiring_sha256"]
+        if "slot_wires_list" in rec:
+            assert [list(ws) for ws in d.wiring.slot_wires_list] == rec["slot_wires_list"]
+            assert [b.name for b in d.boxes] == rec["box_names"]
+
+
+def test_circuits_match_reference_wirings():
+    made = {"half_adder": bc.half_adder, "full_adder": bc.full_adder}
+    g = load_golden("instances.json")
+    for rec in g["circuits"]:
+        name = rec["name"]
+        if name not in made:
+            fn, arg = name[:-1].split("(")
+            made[name] = getattr(bc, fn)(int(arg))
+        f = made[name].flatten()
+        assert (f.wiring.num_wires, len(f.blocks), f.num_ports) == (rec["num_wires"], rec["num_blocks"], rec["num_ports"])
+        assert _digest(f.wiring) == rec["wiring_sha256"] and list(f.wiring.out_wires) == rec["out_wires"]
+    for name, tensor in g["gates"].items():
+        assert getattr(bc, name).tensor.tolist() == tensor  # G6 and friends
+
+
+def test_dimacs_parser_golden():
+    """examples/test_dimacs_parser.py:3-64 plus every file of the SAT test set."""
+    for rec in load_golden("instances.json")["dimacs"]:
+        with open(os.path.join(GOLDEN, "kissat", rec["name"] + ".cnf")) as f:
+            c = CNFInstance.from_dimacs(f.read())
+        assert (c.num_vars, len(c.clauses)) == (rec["num_vars"], rec["num_clauses"])
+        assert hashlib.sha256(json.dumps(c.clauses).encode()).hexdigest() == rec["clauses_sha256"]
+        if "clauses" in rec:
+            assert [list(cl) for cl in c.clauses] == rec["clauses"]
+        assert CNFInstance.from_dimacs(c.to_dimacs()).clauses == c.clauses
+    with pytest.raises(ValueError):
+        CNFInstance.from_dimacs("c nothing\n1 2 0\n")
+    with pytest.raises(ValueError):
+        CNFInstance.from_dimacs("p cnf 2 2\n1 2 0\n")
+    with pytest.raises(ValueError):
+        CNFInstance.from_dimacs("p cnf 1 1\n1 2 0\n")
+
+
+def test_inputs_and_validation():
+    c = CNFInstance.random(3, 5, 8, rng=1)
+    d = c.inputs("01?0?")
+    assert [b.name for b in d.boxes] == ["bit_0", "bit_1", "bit_unk", "bit_0", "bit_unk"]
+    assert c.inputs(5).wiring == c.inputs("00101").wiring
+    with pytest.raises(ValueError):
+        c.inputs("01")
+    with pytest.raises(ValueError):
+        c.inputs("01x0?")
+    with pytest.raises(ValueError):
+        CNFInstance.random(3, 2, 4)
+    with pytest.raises(ValueError):
+        CNFInstance(2, [[1, 3]])
+
+
+def test_path_conventions_roundtrip():
+    rng = np.random.default_rng(0)
+    for L in (2, 3, 7, 20):
+        ids = list(range(L))
+        ssa = []
+        nxt = L
+        while len(ids) > 1:
+            a, b = rng.choice(len(ids), size=2, replace=False)
+            x, y = ids[a], ids[b]
+            ssa.append((x, y))
+            ids = [i for i in ids if i not in (x, y)] + [nxt]
+            nxt += 1
+        lin = ssa_to_linear(ssa, L)
+        assert linear_to_ssa(lin, L) == tuple(ssa)
+
+
+def test_tree_stats_match_reference_cost_model():
+    """cotengra statistics the reference prints for 3-SAT n=4 m=4 rng=0 (02-random-ksat.ipynb:310-314):
+    N = 19 tensors, max tensor 16 B.  (ops / write depend on the tree: 232 ops, 132 B there.)"""
+    c = CNFInstance.random(3, 4, 4, rng=0)
+    d = c.diagram().flatten()
+    tree = find_tree_elimination(Network.from_diagram(d), trials=4, seed=0)
+    st = tree.stats()
+    assert len(d.blocks) == 19 and st.num_contractions == 18
+    assert st.log2_max_size == 4.0
+    assert 2.0 ** st.log2_write <= 2 * 132 and 2.0 ** st.log2_ops <= 4 * 232
+    t2 = ContractionTree.loads(tree.dumps())
+    assert t2.ssa_path == tree.ssa_path and t2.stats().log2_ops == st.log2_ops
+
+
+def test_tree_search_and_slicing():
+    c = CNFInstance.random(3, 30, 128, rng=0)
+    d = (c.inputs(None) >> c.diagram()).flatten()
+    net = Network.from_diagram(d)
+    e = find_tree_elimination(net, trials=4, seed=0)
+    g = find_tree(net, trials=2, seed=0)
+    assert e.stats().num_contractions == g.stats().num_contractions == net.num_leaves - 1
+    assert e.width() <= 24
+    s = e.slice_to(e.width() - 4)
+    assert s.num_slices >= 16 and s.width() <= e.width() - 4
+    assert s.stats().log2_ops < e.stats().log2_ops + 2.0
+    with pytest.raises(ValueError):
+        ContractionTree(net, e.ssa_path[:-1])
+    with pytest.raises(ValueError):
+        ContractionTree(net, e.ssa_path, sliced_wires=(1, 1))
+    with pytest.raises(ValueError):
+        ContractionTree(net, ((0, 0),) + e.ssa_path[1:])
+
+
+def test_slice_blocks_partition_all_slices():
+    from tensorsat_b200.distributed import slice_block
+
+    for n in (1, 5, 64, 100):
+        for w in (1, 2, 3, 8):
+            blocks = [slice_block(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+    with pytest.raises(ValueError):
+        slice_block(4, 2, 2)
