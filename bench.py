@@ -6,8 +6,8 @@ bench.py — contraction-phase benchmark of the B200 executor (contract: see the
 
 Workload (every N): BASELINE config 1, random 3-SAT n=50 m=213 (ratio 4.26) seed 0, SAT decision
 with all inputs unknown, the reference's bintree network (1008 leaf tensors, 795 wires); an
-elimination-order contraction tree sliced to 2^28-entry intermediates = 64 slices.  A "step" is
-one whole contraction (shared part + all 64 slices + combine); with N GPUs the 64 slices are split
+elimination-order contraction tree sliced to 2^30-entry intermediates = 16 slices.  A "step" is
+one whole contraction (shared part + all 16 slices + combine); with N GPUs the 16 slices are split
 into contiguous blocks, one per rank, and combined by one NCCL all-reduce (max).  Total work is
 fixed, so scaling is "strong"; the metric is the contraction time in seconds.
 
@@ -32,8 +32,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_VARS, N_CLAUSES, SEED, K_SAT = 50, 213, 0, 3
-TARGET_LOG2 = 28
-PLAN_FILE = os.path.join(ROOT, "bench_plans", "c1_n50_m213_seed0.json")
+TARGET_LOG2 = 30
+PLAN_FILE = os.path.join(ROOT, "bench_plans", f"c1_n50_m213_seed0_w{TARGET_LOG2}.json")
 WORKLOAD = (f"random {K_SAT}-SAT n={N_VARS} m={N_CLAUSES} seed={SEED}, SAT decision (all inputs unknown), "
             f"bintree network, elimination-order tree sliced to 2^{TARGET_LOG2}-entry intermediates")
 

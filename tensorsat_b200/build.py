@@ -19,7 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtsb.so")
-SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu"]
+SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu", "tsb_merge_sat.cu", "tsb_merge_gen.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -51,7 +51,7 @@ def all_deps() -> list[str]:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(LIB, all_deps()):
         return LIB
-    objs = []
+    objs, procs = [], []
     for src in sources():
         obj = src[:-3] + ".o"
         if force or _stale(obj, all_deps()):
@@ -59,8 +59,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
                    "--expt-relaxed-constexpr", "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
-            subprocess.run(cmd, check=True)
+            procs.append((src, subprocess.Popen(cmd)))  # translation units compile in parallel
         objs.append(obj)
+    for src, proc in procs:
+        if proc.wait() != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
     subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcuda"], check=True)
     return LIB
 

@@ -70,6 +70,63 @@ k_generic(const __grid_constant__ GenDesc d, const void* __restrict__ lhs,
   }
 }
 
+// ---- batched small ops ---------------------------------------------------------------------
+// One CTA per op: the thousands of leaf preparations and rank <= ~14 steps at the bottom (and the
+// tail) of a contraction tree are launch-latency bound, so every wave of mutually
+// independent small ops of a plan is ONE launch.  Same arithmetic as k_generic; operands are
+// addressed through a pointer table (arena base, result buffer, leaf tensors) so that the op list
+// is built once per plan.
+constexpr int kSmallMaxDims = 12;
+constexpr int kSmallThreads = 64;
+
+struct SmallOp {
+  int32_t n_free, n_red, n_out_iter, n_red_iter;
+  int32_t ext[kSmallMaxDims], sl[kSmallMaxDims], sr[kSmallMaxDims], so[kSmallMaxDims];
+  int32_t lhs_buf, rhs_buf, out_buf;  // indices into the pointer table
+  int32_t zero_first;                 // number of output elements to clear first (repeated labels)
+  int64_t lhs_off, rhs_off, out_off;  // byte offsets
+  int8_t dl, dr, dout, clamp, has_rhs, pad0, pad1, pad2;
+};
+
+static __global__ void __launch_bounds__(kSmallThreads)
+k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
+  const SmallOp& d = ops[blockIdx.x];
+  const void* lhs = (const uint8_t*)ptrs[d.lhs_buf] + d.lhs_off;
+  const void* rhs = d.has_rhs ? (const void*)((const uint8_t*)ptrs[d.rhs_buf] + d.rhs_off) : nullptr;
+  void* out = (uint8_t*)ptrs[d.out_buf] + d.out_off;
+  if (d.zero_first) {
+    for (int i = threadIdx.x; i < d.zero_first; i += blockDim.x) store_from_i64(out, d.dout, i, 0);
+    __syncthreads();
+  }
+  for (int it = threadIdx.x; it < d.n_out_iter; it += blockDim.x) {
+    int ol = 0, orr = 0, oo = 0, rem = it;
+    for (int f = d.n_free - 1; f >= 0; f--) {
+      const int e = d.ext[f];
+      const int i = rem % e;
+      rem /= e;
+      ol += i * d.sl[f];
+      orr += i * d.sr[f];
+      oo += i * d.so[f];
+    }
+    int64_t acc = 0;
+    for (int r = 0; r < d.n_red_iter; r++) {
+      int pl = ol, pr = orr, rr = r;
+      for (int q = d.n_free + d.n_red - 1; q >= d.n_free; q--) {
+        const int e = d.ext[q];
+        const int i = rr % e;
+        rr /= e;
+        pl += i * d.sl[q];
+        pr += i * d.sr[q];
+      }
+      const int64_t a = load_as_i64(lhs, d.dl, pl);
+      const int64_t b = d.has_rhs ? load_as_i64(rhs, d.dr, pr) : 1;
+      acc += a * b;
+    }
+    if (d.clamp) acc = acc != 0;
+    store_from_i64(out, d.dout, oo, acc);
+  }
+}
+
 // ---- elementwise -------------------------------------------------------------------------
 
 // out = a | b (u8 0/1, vectorised) — FinRel._union (tensorsat/lang/fin_rel.py:345-346)

@@ -416,6 +416,7 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
   return m;
 }
 
+#ifdef TSB_MERGE_GENERIC_IMPL
 template <typename TL, typename TR, typename TO>
 inline void launch_merge_t(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, bool clamp,
                            cudaStream_t stream) {
@@ -446,13 +447,30 @@ inline void launch_merge_r(tsb_ctx* ctx, const MergeDesc& d, const void* l, cons
   else if (dr == TSB_I32) launch_merge_o<TL, int32_t>(ctx, d, l, r, o, dout, clamp, s);
   else launch_merge_o<TL, int64_t>(ctx, d, l, r, o, dout, clamp, s);
 }
+#endif
+
+bool merge_sat_supported(const MergeDesc& d);
+void launch_merge_sat(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, cudaStream_t stream);
+void launch_merge_generic(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
+                          int dout, bool clamp, cudaStream_t s);
 
 inline void launch_merge(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
                          int dout, bool clamp, cudaStream_t s) {
+  if (clamp && dl == TSB_U8 && dr == TSB_U8 && dout == TSB_U8 && merge_sat_supported(d)) {
+    launch_merge_sat(ctx, d, l, r, o, s);
+    return;
+  }
+  launch_merge_generic(ctx, d, l, dl, r, dr, o, dout, clamp, s);
+}
+
+#ifdef TSB_MERGE_GENERIC_IMPL
+void launch_merge_generic(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
+                          int dout, bool clamp, cudaStream_t s) {
   if (!d.has_rhs) dr = TSB_U8;
   if (dl == TSB_U8) launch_merge_r<uint8_t>(ctx, d, l, r, o, dr, dout, clamp, s);
   else if (dl == TSB_I32) launch_merge_r<int32_t>(ctx, d, l, r, o, dr, dout, clamp, s);
   else launch_merge_r<int64_t>(ctx, d, l, r, o, dr, dout, clamp, s);
 }
+#endif
 
 }  // namespace tsb

@@ -52,6 +52,35 @@ static int64_t numel(const int32_t* ext, int rank) {
   return n;
 }
 
+// Generic-kernel descriptor of an einsum-like pairwise step (any extents, repeated / dropped labels).
+GenDesc lower_generic_contract(int lhs_rank, const int32_t* lhs_wires, int rhs_rank, const int32_t* rhs_wires,
+                               int out_rank, const int32_t* out_wires, const int32_t* wext, int dl, int dr, int dout,
+                               bool clamp, bool accumulate, bool& out_dups) {
+  std::vector<int32_t> le(lhs_rank), re(rhs_rank), oe(out_rank);
+  for (int i = 0; i < lhs_rank; i++) le[i] = wext[lhs_wires[i]];
+  for (int i = 0; i < rhs_rank; i++) re[i] = wext[rhs_wires[i]];
+  for (int i = 0; i < out_rank; i++) oe[i] = wext[out_wires[i]];
+  std::map<int32_t, LDim> dims;
+  auto ls = c_strides(le.data(), lhs_rank), rs = c_strides(re.data(), rhs_rank), os = c_strides(oe.data(), out_rank);
+  for (int i = 0; i < lhs_rank; i++) {
+    LDim& d = dims[lhs_wires[i]];
+    d.label = lhs_wires[i]; d.ext = le[i]; d.sl += ls[i]; d.in_l = true;
+  }
+  for (int i = 0; i < rhs_rank; i++) {
+    LDim& d = dims[rhs_wires[i]];
+    d.label = rhs_wires[i]; d.ext = re[i]; d.sr += rs[i]; d.in_r = true;
+  }
+  out_dups = false;
+  for (int i = 0; i < out_rank; i++) {
+    LDim& d = dims[out_wires[i]];
+    if (d.in_o) out_dups = true;
+    d.so += os[i]; d.in_o = true;
+  }
+  std::vector<LDim> v;
+  for (auto& kv : dims) v.push_back(kv.second);
+  return make_gen_desc(v, dl, dr, dout, clamp, true, accumulate);
+}
+
 // ---------------------------------------------------------------------------------------------
 // contract2 (FinRel._contract2, tensorsat/lang/fin_rel.py:255-288)
 // ---------------------------------------------------------------------------------------------
@@ -127,26 +156,10 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
   }
 
   // ---- generic path
-  std::map<int32_t, LDim> dims;
-  auto ls = c_strides(le.data(), lhs_rank), rs = c_strides(re.data(), rhs_rank), os = c_strides(oe.data(), out_rank);
-  for (int i = 0; i < lhs_rank; i++) {
-    LDim& d = dims[lhs_wires[i]];
-    d.label = lhs_wires[i]; d.ext = le[i]; d.sl += ls[i]; d.in_l = true;
-  }
-  for (int i = 0; i < rhs_rank; i++) {
-    LDim& d = dims[rhs_wires[i]];
-    d.label = rhs_wires[i]; d.ext = re[i]; d.sr += rs[i]; d.in_r = true;
-  }
   bool out_dups = false;
-  for (int i = 0; i < out_rank; i++) {
-    LDim& d = dims[out_wires[i]];
-    if (d.in_o) out_dups = true;
-    d.so += os[i]; d.in_o = true;
-  }
-  std::vector<LDim> v;
-  for (auto& kv : dims) v.push_back(kv.second);
+  GenDesc g = lower_generic_contract(lhs_rank, lhs_wires, rhs_rank, rhs_wires, out_rank, out_wires, wext, dl, dr, dout,
+                                     clamp, accumulate, out_dups);
   if (out_dups && !accumulate) TSB_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * dtype_size(dout), stream));
-  GenDesc g = make_gen_desc(v, dl, dr, dout, clamp, true, accumulate);
   launch_generic(ctx, g, lhs, rhs, out, stream);
 }
 

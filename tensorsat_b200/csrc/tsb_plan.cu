@@ -27,6 +27,9 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
 void rewire_impl(tsb_ctx* ctx, const void* src, int src_rank, const int32_t* sext, const int32_t* fixed_idx, int ds,
                  void* dst, int out_rank, const int32_t* out_ports, int dd, bool clamp, bool accumulate,
                  cudaStream_t stream);
+GenDesc lower_generic_contract(int lhs_rank, const int32_t* lhs_wires, int rhs_rank, const int32_t* rhs_wires,
+                               int out_rank, const int32_t* out_wires, const int32_t* wext, int dl, int dr, int dout,
+                               bool clamp, bool accumulate, bool& out_dups);
 
 struct PNode {
   std::vector<int32_t> slab;     // sliced wires present below this node (order of desc.sliced_wires)
@@ -39,9 +42,11 @@ struct PNode {
   int64_t offset = -1;           // byte offset in the arena block (-1: not allocated / external)
   size_t bytes = 0;
   bool is_out = false;           // the root, written straight into the caller's buffer
+  bool post = false;             // shared node computed AFTER the slice loop (tail of the tree)
+  bool gathered = false;         // per-slice node stored with the sliced wires leading: slice s fills block s
   std::vector<int32_t> stored() const {  // axis order of the stored buffer
     std::vector<int32_t> v;
-    if (shared) v = slab;
+    if (shared || gathered) v = slab;
     v.insert(v.end(), reg.begin(), reg.end());
     return v;
   }
@@ -62,6 +67,19 @@ struct POp {
   std::vector<int32_t> leaf_ports;  // dst axis j <- leaf axis leaf_ports[j]
   double alg_bytes = 0, alg_ops = 0;
   int b = 0, m = 0, n = 0, k = 0;  // label class sizes in bits (for reports)
+  float last_ms = 0;
+  // generic-kernel descriptor, lowered once at plan time
+  bool has_gd = false, gd_zero = false;
+  GenDesc gd{};
+  bool small = false;  // runs inside a k_small_batch launch
+  int wave = 0;        // dependency depth among the once-only ops
+};
+
+struct Launch {   // one entry of the once-only schedule
+  int wave = 0;
+  int op = -1;          // single op, or
+  int batch_begin = 0;  // [begin, end) into the small-op array
+  int batch_end = 0;
   float last_ms = 0;
 };
 
@@ -85,6 +103,14 @@ struct tsb_plan {
   std::vector<int32_t> rbuf_axes;
   bool timing = false;
   std::vector<cudaEvent_t> ev;
+  std::vector<Launch> schedule;        // once-only part before the slice loop, in launch order
+  std::vector<Launch> post_schedule;   // once-only part after the slice loop (re-batched tail of the tree)
+  std::vector<int> gathered_nodes;     // zero-filled before the slice loop
+  std::vector<int> slice_ops;          // per-slice ops, in order
+  std::vector<SmallOp> small_ops;      // host copy
+  SmallOp* d_small_ops = nullptr;
+  void** d_ptrs = nullptr;             // device pointer table: [arena, out, leaf 0, leaf 1, ...]
+  void** h_ptrs = nullptr;             // pinned staging of the table
 };
 
 namespace {
@@ -271,7 +297,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   };
 
   // ---- nodes ---------------------------------------------------------------------------------
-  const int batch_log2 = D.batch_log2 >= 0 ? D.batch_log2 : 18;
+  const int batch_log2 = D.batch_log2 >= 0 ? D.batch_log2 : 24;
   P.nodes.resize(2 * L - 1);
   const bool sliced_any = !P.sliced.empty();
   for (int i = 0; i < 2 * L - 1; i++) {
@@ -290,6 +316,44 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       nd.shared = P.nodes[pr.first].shared && P.nodes[pr.second].shared && lg <= batch_log2 && i != P.root;
     }
   }
+  // sliced output wires: per-slice results are stacked into an intermediate buffer
+  for (auto w : P.out_wires) if (S.count(w)) P.stack_out = true;
+  // Tail of the tree: once the per-slice tensors are small again (with the sliced wires kept), the slices
+  // are gathered into one tensor and the remaining steps run ONCE after the slice loop.
+  if (sliced_any && n_steps > 0 && !P.stack_out) {
+    std::vector<int> parent(2 * L - 1, -1);
+    for (int s = 0; s < n_steps; s++) { parent[path[s].first] = L + s; parent[path[s].second] = L + s; }
+    auto lg_b = [&](int i) { return std::log2((double)P.nodes[i].reg_numel) + std::log2((double)P.nodes[i].s_numel); };
+    for (int i = 2 * L - 2; i >= L; i--) {
+      PNode& nd = P.nodes[i];
+      if (nd.shared) continue;
+      const bool parent_post = i == P.root || P.nodes[parent[i]].post;
+      nd.post = parent_post && lg_b(i) <= batch_log2;
+    }
+    // a post node may not gather a child that is huge once all its slices are kept
+    for (int i = L; i <= 2 * L - 2; i++) {
+      PNode& nd = P.nodes[i];
+      if (!nd.post) continue;
+      for (int c : {path[i - L].first, path[i - L].second})
+        if (!P.nodes[c].shared && !P.nodes[c].post && lg_b(c) > batch_log2 + 6) nd.post = false;
+    }
+    // post status must be upward closed: a node whose parent lost it keeps it only if the parent still has it
+    for (int i = 2 * L - 2; i >= L; i--)
+      if (P.nodes[i].post && i != P.root && !P.nodes[parent[i]].post) {
+        // parent runs per slice: this node would have to be per slice as well
+        P.nodes[i].post = false;
+      }
+    for (int i = L; i <= 2 * L - 2; i++) {
+      PNode& nd = P.nodes[i];
+      if (nd.post) { nd.shared = true; continue; }
+      if (!nd.shared && i != P.root && P.nodes[parent[i]].post) nd.gathered = true;
+    }
+    if (P.nodes[P.root].post) {
+      // the sliced wires are ordinary summed wires of the last step: the result carries none of them
+      P.nodes[P.root].slab.clear();
+      P.nodes[P.root].s_numel = 1;
+    }
+  }
   if (P.mode == TSB_COUNT) {
     P.nodes[P.root].dtype = TSB_I64;
     double tot = bound[P.root];
@@ -297,9 +361,6 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     P.info.may_overflow = tot > 62.0;
     for (int i = 0; i < 2 * L - 1; i++) if (bound[i] > 62.0) P.info.may_overflow = 1;
   }
-  // sliced output wires: per-slice results are stacked into an intermediate buffer
-  for (auto w : P.out_wires) if (S.count(w)) P.stack_out = true;
-
   // ---- ops -----------------------------------------------------------------------------------
   auto esz = [&](int node) { return (int64_t)dtype_size(P.nodes[node].dtype); };
   for (int i = 0; i < L; i++) {
@@ -352,47 +413,101 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   }
   if (n_steps > 0 && !P.stack_out) P.nodes[P.root].is_out = true;
 
-  // fast-kernel eligibility of each step
+  // ---- kernel selection ------------------------------------------------------------------------
   const bool force_generic = (P.flags & TSB_PLAN_FORCE_GENERIC) != 0;
+  const bool clamp = P.mode == TSB_SAT;
   for (auto& op : P.ops) {
-    if (op.kind != OP_STEP || force_generic) continue;
-    bool pow2 = true;
-    for (auto w : op.lw) pow2 = pow2 && is_pow2(P.wext[w]);
-    for (auto w : op.rw) pow2 = pow2 && is_pow2(P.wext[w]);
-    if (!pow2) continue;
-    BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
-    BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
-    BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
-    MergeArgs m = make_merge_desc(lb, &rb, ob, false);
-    if (m.ok) {
-      op.use_merge = true;
-      op.md = m.d;
+    const PNode& o = P.nodes[op.out];
+    const int64_t out_numel = prod_ext(op.kind == OP_LEAF ? o.stored() : op.ow, P.wext);
+    if (op.kind == OP_STEP && !force_generic && out_numel > 4096) {
+      bool pow2 = true;
+      for (auto w : op.lw) pow2 = pow2 && is_pow2(P.wext[w]);
+      for (auto w : op.rw) pow2 = pow2 && is_pow2(P.wext[w]);
+      if (pow2) {
+        BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
+        BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
+        BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
+        MergeArgs m = make_merge_desc(lb, &rb, ob, false);
+        if (m.ok) {
+          op.use_merge = true;
+          op.md = m.d;
+        }
+      }
+    }
+    if (op.use_merge) continue;
+    // generic kernel: lowered once, here (the root of a sliced plan accumulates and stays on the slow path)
+    if (op.kind == OP_LEAF) {
+      const auto& lw = P.leaf_wires[op.leaf];
+      const std::vector<int32_t> ow = o.stored();
+      op.gd = lower_generic_contract((int)lw.size(), lw.data(), 0, nullptr, (int)ow.size(), ow.data(), P.wext.data(),
+                                     TSB_U8, TSB_U8, o.dtype, clamp, false, op.gd_zero);
+      op.gd.has_rhs = 0;
+      op.has_gd = true;
+    } else if (!(op.per_slice && op.out == P.root)) {
+      op.gd = lower_generic_contract((int)op.lw.size(), op.lw.data(), (int)op.rw.size(), op.rw.data(),
+                                     (int)op.ow.size(), op.ow.data(), P.wext.data(), P.nodes[op.lhs].dtype,
+                                     P.nodes[op.rhs].dtype, o.dtype, clamp, false, op.gd_zero);
+      op.has_gd = true;
+    }
+    if (op.has_gd && !op.per_slice && !(P.n_leaves == 1 && sliced_any)) {
+      const GenDesc& g = op.gd;
+      bool ok = g.n_free + g.n_red <= kSmallMaxDims && g.n_out_iter <= (1 << 14) && g.n_red_iter <= (1 << 12);
+      for (int q = 0; ok && q < g.n_free + g.n_red; q++)
+        ok = g.sl[q] < (int64_t(1) << 30) && g.sr[q] < (int64_t(1) << 30) && g.so[q] < (int64_t(1) << 30);
+      op.small = ok;
     }
   }
 
-  // ---- memory plan -----------------------------------------------------------------------------
-  // timeline: shared ops in order, then the per-slice ops in order (repeated for every slice)
-  std::vector<int> order;
-  for (int i = 0; i < (int)P.ops.size(); i++) if (!P.ops[i].per_slice) order.push_back(i);
-  for (int i = 0; i < (int)P.ops.size(); i++) if (P.ops[i].per_slice) order.push_back(i);
-  std::vector<int> last_use(P.nodes.size(), -1);
-  for (int t = 0; t < (int)order.size(); t++) {
-    const POp& op = P.ops[order[t]];
-    if (op.lhs >= 0) last_use[op.lhs] = t;
-    if (op.rhs >= 0) last_use[op.rhs] = t;
+  // ---- schedule of the once-only parts: waves of mutually independent ops ---------------------------
+  // pre = before the slice loop, post = after it (tail of the tree on gathered slices)
+  std::vector<int> producer(P.nodes.size() + 1, -1);
+  for (int i = 0; i < (int)P.ops.size(); i++) producer[P.ops[i].out] = i;
+  auto is_post_op = [&](const POp& op) { return !op.per_slice && P.nodes[op.out].post; };
+  for (auto& op : P.ops) {
+    if (op.per_slice) continue;
+    const bool post = is_post_op(op);
+    int w = 0;
+    for (int opnd : {op.lhs, op.rhs})
+      if (opnd >= 0 && producer[opnd] >= 0) {
+        const POp& pr = P.ops[producer[opnd]];
+        if (!pr.per_slice && is_post_op(pr) == post) w = std::max(w, pr.wave + 1);
+      }
+    op.wave = w;
   }
-  // shared tensors consumed by per-slice ops must survive every slice iteration
-  const int T_END = (int)order.size();
-  for (auto& op : P.ops)
-    if (op.per_slice) {
-      if (op.lhs >= 0 && P.nodes[op.lhs].shared) last_use[op.lhs] = T_END;
-      if (op.rhs >= 0 && P.nodes[op.rhs].shared) last_use[op.rhs] = T_END;
-    }
-  FreeList fl;
+  std::vector<int> pre_ops, post_ops;
+  for (int i = 0; i < (int)P.ops.size(); i++) {
+    if (P.ops[i].per_slice) P.slice_ops.push_back(i);
+    else (is_post_op(P.ops[i]) ? post_ops : pre_ops).push_back(i);
+  }
+  auto by_wave = [&](int a, int b) { return P.ops[a].wave < P.ops[b].wave; };
+  std::stable_sort(pre_ops.begin(), pre_ops.end(), by_wave);
+  std::stable_sort(post_ops.begin(), post_ops.end(), by_wave);
+
+  // ---- memory plan -----------------------------------------------------------------------------
+  // timeline: [pre waves][per-slice ops, repeated for every slice][post waves]; ops of one wave run
+  // concurrently.  Whatever must survive from one slice iteration to the next (shared operands of the
+  // loop, gathered results) is allocated outside the loop's reusable region.
   for (int i = 0; i < (int)P.nodes.size(); i++) {
     PNode& nd = P.nodes[i];
-    nd.bytes = (size_t)(nd.reg_numel * (nd.shared ? nd.s_numel : 1) * dtype_size(nd.dtype));
+    nd.bytes = (size_t)(nd.reg_numel * ((nd.shared || nd.gathered) ? nd.s_numel : 1) * dtype_size(nd.dtype));
   }
+  const int n_pre = pre_ops.empty() ? 0 : P.ops[pre_ops.back()].wave + 1;
+  const int n_loop = (int)P.slice_ops.size();
+  const int n_post = post_ops.empty() ? 0 : P.ops[post_ops.back()].wave + 1;
+  std::vector<int> tpos(P.ops.size(), 0);
+  for (int i : pre_ops) tpos[i] = P.ops[i].wave;
+  for (int q = 0; q < n_loop; q++) tpos[P.slice_ops[q]] = n_pre + q;
+  for (int i : post_ops) tpos[i] = n_pre + n_loop + P.ops[i].wave;
+  const int T_END = n_pre + n_loop + n_post;
+  std::vector<int> last_use(P.nodes.size(), -1);
+  for (int i = 0; i < (int)P.ops.size(); i++)
+    for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+      if (opnd >= 0) last_use[opnd] = std::max(last_use[opnd], tpos[i]);
+  // shared tensors consumed inside the loop must survive every slice iteration
+  for (int i : P.slice_ops)
+    for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+      if (opnd >= 0 && P.nodes[opnd].shared) last_use[opnd] = std::max(last_use[opnd], n_pre + n_loop - 1);
+  FreeList fl;
   if (P.stack_out || (sliced_any && L == 1)) {
     // result buffer with the sliced output wires leading; combined across slices, permuted at the end
     PNode r;
@@ -408,14 +523,95 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     P.nodes.push_back(r);
     P.stack_out = true;
   }
-  for (int t = 0; t < (int)order.size(); t++) {
-    POp& op = P.ops[order[t]];
-    PNode& o = P.nodes[op.out];
-    if (!o.is_out) o.offset = fl.alloc((int64_t)o.bytes);
-    for (int opnd : {op.lhs, op.rhs})
-      if (opnd >= 0 && last_use[opnd] == t && P.nodes[opnd].offset >= 0) fl.release(P.nodes[opnd].offset, (int64_t)P.nodes[opnd].bytes);
+  {
+    std::vector<std::vector<int>> at(T_END + 1);
+    for (int i = 0; i < (int)P.ops.size(); i++) at[tpos[i]].push_back(i);
+    for (int t = 0; t < T_END; t++) {
+      if (t == n_pre) {
+        for (int i = 0; i < 2 * L - 1; i++)
+          if (P.nodes[i].gathered) {
+            P.nodes[i].offset = fl.alloc((int64_t)P.nodes[i].bytes);
+            P.gathered_nodes.push_back(i);
+          }
+      }
+      for (int i : at[t]) {
+        PNode& o = P.nodes[P.ops[i].out];
+        if (!o.is_out && !o.gathered) o.offset = fl.alloc((int64_t)o.bytes);
+      }
+      std::set<int> freed;
+      for (int i : at[t])
+        for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+          if (opnd >= 0 && last_use[opnd] == t && P.nodes[opnd].offset >= 0 && !freed.count(opnd)) {
+            fl.release(P.nodes[opnd].offset, (int64_t)P.nodes[opnd].bytes);
+            freed.insert(opnd);
+          }
+      if (t == n_pre + n_loop - 1) {
+        // end of the loop: shared operands whose last consumer was inside the loop, at an earlier position
+        for (int nd = 0; nd < 2 * L - 1; nd++)
+          if (P.nodes[nd].shared && P.nodes[nd].offset >= 0 && last_use[nd] == t && !freed.count(nd)) {
+            bool used_here = false;
+            for (int i : at[t]) used_here = used_here || P.ops[i].lhs == nd || P.ops[i].rhs == nd;
+            if (!used_here) { fl.release(P.nodes[nd].offset, (int64_t)P.nodes[nd].bytes); freed.insert(nd); }
+          }
+      }
+    }
   }
   P.info.peak_bytes = fl.peak;
+
+  // ---- launch schedules + small-op table ------------------------------------------------------------
+  auto buf_of = [&](int node, int32_t& buf, int64_t& off) {
+    const PNode& nd = P.nodes[node];
+    if (nd.is_out) { buf = 1; off = 0; }
+    else { buf = 0; off = nd.offset; }
+  };
+  auto build_schedule = [&](const std::vector<int>& ops, int n_waves, std::vector<Launch>& sched) {
+    for (int w = 0; w < n_waves; w++) {
+      Launch batch;
+      batch.wave = w;
+      batch.batch_begin = (int)P.small_ops.size();
+      for (int i : ops) {
+        POp& op = P.ops[i];
+        if (op.wave != w || !op.small) continue;
+        const GenDesc& g = op.gd;
+        SmallOp so{};
+        so.n_free = g.n_free; so.n_red = g.n_red;
+        so.n_out_iter = (int32_t)g.n_out_iter; so.n_red_iter = (int32_t)g.n_red_iter;
+        for (int q = 0; q < g.n_free + g.n_red; q++) {
+          so.ext[q] = g.ext[q]; so.sl[q] = (int32_t)g.sl[q]; so.sr[q] = (int32_t)g.sr[q]; so.so[q] = (int32_t)g.so[q];
+        }
+        so.dl = (int8_t)g.dl; so.dr = (int8_t)g.dr; so.dout = (int8_t)g.dout;
+        so.clamp = (int8_t)g.clamp; so.has_rhs = (int8_t)g.has_rhs;
+        const PNode& o = P.nodes[op.out];
+        so.zero_first = op.gd_zero ? (int32_t)(o.bytes / dtype_size(o.dtype)) : 0;
+        buf_of(op.out, so.out_buf, so.out_off);
+        if (op.kind == OP_LEAF) {
+          so.lhs_buf = 2 + op.leaf; so.lhs_off = 0;
+          so.rhs_buf = 0; so.rhs_off = 0;
+        } else {
+          buf_of(op.lhs, so.lhs_buf, so.lhs_off);
+          buf_of(op.rhs, so.rhs_buf, so.rhs_off);
+        }
+        P.small_ops.push_back(so);
+      }
+      batch.batch_end = (int)P.small_ops.size();
+      if (batch.batch_end > batch.batch_begin) sched.push_back(batch);
+      for (int i : ops) {
+        if (P.ops[i].wave != w || P.ops[i].small) continue;
+        Launch l;
+        l.wave = w;
+        l.op = i;
+        sched.push_back(l);
+      }
+    }
+  };
+  build_schedule(pre_ops, n_pre, P.schedule);
+  build_schedule(post_ops, n_post, P.post_schedule);
+  if (!P.small_ops.empty()) {
+    TSB_CUDA(cudaMalloc((void**)&P.d_small_ops, P.small_ops.size() * sizeof(SmallOp)));
+    TSB_CUDA(cudaMemcpy(P.d_small_ops, P.small_ops.data(), P.small_ops.size() * sizeof(SmallOp), cudaMemcpyHostToDevice));
+  }
+  TSB_CUDA(cudaMalloc((void**)&P.d_ptrs, (size_t)(L + 2) * sizeof(void*)));
+  TSB_CUDA(cudaMallocHost((void**)&P.h_ptrs, (size_t)(L + 2) * sizeof(void*)));
 
   // ---- info ------------------------------------------------------------------------------------
   P.info.n_slices = prod_ext(P.sliced, P.wext);
@@ -423,13 +619,13 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   P.info.out_dtype = P.mode == TSB_SAT ? TSB_U8 : TSB_I64;
   P.info.n_steps = n_steps;
   int mx = 0;
+  P.info.n_kernels_shared = (int)(P.schedule.size() + P.post_schedule.size());
   for (auto& op : P.ops) {
     if (op.per_slice) {
       P.info.n_kernels_per_slice++;
       P.info.alg_bytes_per_slice += op.alg_bytes;
       P.info.alg_ops_per_slice += op.alg_ops;
     } else {
-      P.info.n_kernels_shared++;
       P.info.alg_bytes_shared += op.alg_bytes;
       P.info.alg_ops_shared += op.alg_ops;
     }
@@ -472,6 +668,7 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     if (b.shared) pr += shared_offset(P, b, *digits) * dtype_size(b.dtype);
   }
   void* po = o.is_out ? out_ptr : (void*)(base + o.offset);
+  if (op.per_slice && o.gathered) po = (uint8_t*)po + shared_offset(P, o, *digits) * dtype_size(o.dtype);
   bool acc = accumulate && o.is_out;
   if (P.stack_out && op.out == P.root) {
     // root result goes into the slice's block of the stacked result buffer, accumulating
@@ -486,6 +683,9 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     MergeDesc d = op.md;
     d.accumulate = acc ? 1 : 0;
     launch_merge(ctx, d, pl, a.dtype, pr, b.dtype, po, dout, clamp, stream);
+  } else if (op.has_gd && !acc && dout == o.dtype) {
+    if (op.gd_zero) TSB_CUDA(cudaMemsetAsync(po, 0, o.bytes, stream));
+    launch_generic(ctx, op.gd, pl, pr, po, stream);
   } else {
     contract2_impl(ctx, pl, (int)op.lw.size(), op.lw.data(), a.dtype, pr, (int)op.rw.size(), op.rw.data(), b.dtype, po,
                    (int)op.ow.size(), op.ow.data(), dout, P.n_wires, P.wext.data(), P.mode, acc,
@@ -499,6 +699,11 @@ void run_leaf(tsb_plan& P, POp& op, uint8_t* base, const void* leaf_ptr, void* o
   const auto& lw = P.leaf_wires[op.leaf];
   const std::vector<int32_t> ow = o.stored();
   void* po = o.is_out ? out_ptr : (void*)(base + o.offset);
+  if (op.has_gd) {
+    if (op.gd_zero) TSB_CUDA(cudaMemsetAsync(po, 0, o.bytes, stream));
+    launch_generic(P.ctx, op.gd, leaf_ptr, nullptr, po, stream);
+    return;
+  }
   contract2_impl(P.ctx, leaf_ptr, (int)lw.size(), lw.data(), TSB_U8, P.ctx->d_one, 0, nullptr, TSB_U8, po,
                  (int)ow.size(), ow.data(), o.dtype, P.n_wires, P.wext.data(), P.mode, false, true, stream);
 }
@@ -539,9 +744,29 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     first = false;
     const PNode& o = plan->nodes[op.out];
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_STEP ? (op.use_merge ? "merge" : "generic") : "permute")
-       << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
+       << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms << "}";
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
+    if (op.kind == OP_STEP && op.ow.size() >= 20) {
+      auto arr = [&](const char* name, const std::vector<int32_t>& v) {
+        os << ",\"" << name << "\":[";
+        for (size_t q = 0; q < v.size(); q++) os << (q ? "," : "") << v[q];
+        os << "]";
+      };
+      arr("lw", op.lw); arr("rw", op.rw); arr("ow", op.ow);
+    }
+    os << "}";
+  }
+  os << "],\"launches\":[";
+  first = true;
+  std::vector<Launch> all = plan->schedule;
+  all.insert(all.end(), plan->post_schedule.begin(), plan->post_schedule.end());
+  for (auto& l : all) {
+    if (!first) os << ",";
+    first = false;
+    os << "{\"wave\":" << l.wave << ",\"op\":" << l.op << ",\"n_small\":" << (l.batch_end - l.batch_begin)
+       << ",\"ms\":" << l.last_ms << "}";
   }
   os << "]}";
   const std::string s = os.str();
@@ -599,17 +824,53 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       const PNode& r = P.nodes[P.rnode];
       TSB_CUDA(cudaMemsetAsync(base + r.offset, 0, r.bytes, stream));
     }
-    // shared part: once
-    for (size_t i = 0; i < P.ops.size(); i++) {
-      POp& op = P.ops[i];
-      if (op.per_slice) continue;
-      if (op.kind == OP_LEAF) {
-        if (P.n_leaves == 1 && !P.sliced.empty()) continue;  // handled per slice below
-        timed(i, [&] { run_leaf(P, op, base, leaf_ptrs[op.leaf], out, stream); });
-      } else {
-        timed(i, [&] { run_step(P, op, base, out, nullptr, false, stream); });
-      }
+    // pointer table for the batched small ops: [arena, out, leaves...]
+    if (!P.small_ops.empty()) {
+      P.h_ptrs[0] = base;
+      P.h_ptrs[1] = out;
+      for (int i = 0; i < P.n_leaves; i++) P.h_ptrs[2 + i] = const_cast<void*>(leaf_ptrs[i]);
+      TSB_CUDA(cudaMemcpyAsync(P.d_ptrs, P.h_ptrs, (size_t)(P.n_leaves + 2) * sizeof(void*), cudaMemcpyHostToDevice,
+                               stream));
     }
+    for (int g : P.gathered_nodes) TSB_CUDA(cudaMemsetAsync(base + P.nodes[g].offset, 0, P.nodes[g].bytes, stream));
+    // once-only parts: waves of independent ops (small ops of a wave = one launch)
+    auto run_schedule = [&](std::vector<Launch>& sched) {
+      for (size_t li = 0; li < sched.size(); li++) {
+        Launch& l = sched[li];
+        l.last_ms = 0;
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (timing) {
+          TSB_CUDA(cudaEventCreate(&t0));
+          TSB_CUDA(cudaEventCreate(&t1));
+          TSB_CUDA(cudaEventRecord(t0, stream));
+        }
+        if (l.op < 0) {
+          const int n = l.batch_end - l.batch_begin;
+          TSB_LAUNCH(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
+                     (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
+          ctx->launches++;
+          TSB_CUDA(cudaGetLastError());
+        } else {
+          POp& op = P.ops[l.op];
+          if (op.kind == OP_LEAF) {
+            if (!(P.n_leaves == 1 && !P.sliced.empty())) run_leaf(P, op, base, leaf_ptrs[op.leaf], out, stream);
+          } else {
+            run_step(P, op, base, out, nullptr, false, stream);
+          }
+        }
+        if (timing) {
+          TSB_CUDA(cudaEventRecord(t1, stream));
+          TSB_CUDA(cudaEventSynchronize(t1));
+          float ms = 0;
+          TSB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+          l.last_ms = ms;
+          if (l.op >= 0) P.ops[l.op].last_ms = ms;
+          cudaEventDestroy(t0);
+          cudaEventDestroy(t1);
+        }
+      }
+    };
+    run_schedule(P.schedule);
     // per-slice part
     if (!P.sliced.empty()) {
       for (int64_t sid = slice_begin; sid < slice_end; sid++) {
@@ -631,13 +892,13 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
                       ports.data(), r.dtype, P.mode == TSB_SAT, true, stream);
           continue;
         }
-        for (size_t i = 0; i < P.ops.size(); i++) {
+        for (int i : P.slice_ops) {
           POp& op = P.ops[i];
-          if (!op.per_slice) continue;
-          timed(i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, stream); });
+          timed((size_t)i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, stream); });
         }
       }
     }
+    run_schedule(P.post_schedule);
     if (P.stack_out) {
       // [sliced output wires][other output wires] -> requested output order
       const PNode& r = P.nodes[P.rnode];
@@ -660,6 +921,9 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
 int tsb_plan_destroy(tsb_plan* plan) {
   if (plan) {
     for (auto e : plan->ev) cudaEventDestroy(e);
+    if (plan->d_small_ops) cudaFree(plan->d_small_ops);
+    if (plan->d_ptrs) cudaFree(plan->d_ptrs);
+    if (plan->h_ptrs) cudaFreeHost(plan->h_ptrs);
     delete plan;
   }
   return TSB_OK;

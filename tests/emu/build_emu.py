@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "tensorsat_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libtsb_emu.so")
-SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu"]
+SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu", "tsb_merge_sat.cu", "tsb_merge_gen.cu"]
 
 
 def build(force: bool = False) -> str:
