@@ -17,28 +17,86 @@ constexpr int kSatThreads = 256;
 struct MergeSatDesc {
   MergeDesc m;
   int32_t stream_l, stream_r;  // operand bytes are used once: load with evict-first
+  // A thread computes the 4 output vectors whose tile-local index differs in bits bit_a < bit_b; the host
+  // picks bits one operand does not depend on, so that operand's vector is loaded once for 2 (or 4) outputs.
+  int32_t bit_a, bit_b;
 };
 
 constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1) + ((x >> 2) & 1) + ((x >> 3) & 1); }
 
+// L2 residency control (126 MB L2 on B200): the operand that every output tile re-reads is loaded with
+// an evict_last policy, the operand / result that stream through once with evict_first, so that the
+// stream does not push the reused operand out of L2 (measured: DRAM traffic back to the algorithmic bytes).
 #ifdef TSB_HOST_EMU
-template <typename T> TSB_D T ld_stream(const T* p) { return *p; }
-template <typename T> TSB_D void st_stream(T* p, T v) { *p = v; }
+TSB_D uint64_t l2_policy(bool) { return 0; }
+TSB_D uint32_t ldg_hint_u8(const uint8_t* p, uint64_t) { return *p; }
+TSB_D uint32_t ldg_hint_u16(const uint8_t* p, uint64_t) { return *(const uint16_t*)p; }
+TSB_D uint32_t ldg_hint_u32(const uint8_t* p, uint64_t) { return *(const uint32_t*)p; }
+TSB_D uint2 ldg_hint_v2(const uint8_t* p, uint64_t) { return *(const uint2*)p; }
+TSB_D uint4 ldg_hint_v4(const uint8_t* p, uint64_t) { return *(const uint4*)p; }
+TSB_D void stg_hint_v4(uint4* p, uint4 v, uint64_t) { *p = v; }
 #else
-template <typename T> TSB_D T ld_stream(const T* p) { return __ldcs(p); }
-template <typename T> TSB_D void st_stream(T* p, T v) { __stcs(p, v); }
+TSB_D uint64_t l2_policy(bool streaming) {
+  uint64_t pol;
+  if (streaming) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+TSB_D uint32_t ldg_hint_u8(const uint8_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+TSB_D uint32_t ldg_hint_u16(const uint8_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+TSB_D uint32_t ldg_hint_u32(const uint8_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+TSB_D uint2 ldg_hint_v2(const uint8_t* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+TSB_D uint4 ldg_hint_v4(const uint8_t* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+TSB_D void stg_hint_v4(uint4* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 #endif
 
-// Loads the 2^popc(NIB) operand bytes one output vector touches and expands them to 16 lanes.
-template <int NIB, bool STREAM>
-TSB_D void load_expand(const uint8_t* p, uint32_t X[4]) {
+// The 2^popc(NIB) operand bytes one output vector touches, as loaded (1..4 registers).
+template <int NIB> struct Raw { uint32_t w[popc4(NIB) <= 2 ? 1 : popc4(NIB) == 3 ? 2 : 4]; };
+
+template <int NIB>
+TSB_D Raw<NIB> raw_load(const uint8_t* p, uint64_t pol) {
+  constexpr int VB = popc4(NIB);
+  Raw<NIB> r;
+  if constexpr (VB == 0) r.w[0] = ldg_hint_u8(p, pol);
+  else if constexpr (VB == 1) r.w[0] = ldg_hint_u16(p, pol);
+  else if constexpr (VB == 2) r.w[0] = ldg_hint_u32(p, pol);
+  else if constexpr (VB == 3) { uint2 t = ldg_hint_v2(p, pol); r.w[0] = t.x; r.w[1] = t.y; }
+  else { uint4 t = ldg_hint_v4(p, pol); r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w; }
+  return r;
+}
+
+// X byte e (0..15) = operand byte pext(e, NIB): the byte output lane e reads.
+template <int NIB>
+TSB_D void expand(const Raw<NIB>& r, uint32_t X[4]) {
   constexpr int VB = popc4(NIB), p0 = NIB & 3, p1 = NIB >> 2;
-  uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-  if constexpr (VB == 0) b0 = STREAM ? ld_stream(p) : *p;
-  else if constexpr (VB == 1) b0 = STREAM ? ld_stream((const uint16_t*)p) : *(const uint16_t*)p;
-  else if constexpr (VB == 2) b0 = STREAM ? ld_stream((const uint32_t*)p) : *(const uint32_t*)p;
-  else if constexpr (VB == 3) { uint2 t = STREAM ? ld_stream((const uint2*)p) : *(const uint2*)p; b0 = t.x; b1 = t.y; }
-  else { uint4 t = STREAM ? ld_stream((const uint4*)p) : *(const uint4*)p; b0 = t.x; b1 = t.y; b2 = t.z; b3 = t.w; }
+  const uint32_t b0 = r.w[0];
+  uint32_t b1 = 0, b2 = 0, b3 = 0;
+  if constexpr (VB >= 3) b1 = r.w[1];
+  if constexpr (VB == 4) { b2 = r.w[2]; b3 = r.w[3]; }
   // groups: the operand bytes selected by lanes 4g..4g+3 of the (at most 4) distinct groups
   uint32_t G0, G1 = 0, G2 = 0, G3 = 0;
   constexpr int NG = 1 << popc4(p1);  // distinct groups needed
@@ -63,47 +121,42 @@ TSB_D void load_expand(const uint8_t* p, uint32_t X[4]) {
   else { X[0] = X[1] = G0; X[2] = X[3] = G1; }
 }
 
-template <int NIBL, int NIBR>
-TSB_D void merge_sat_body(const MergeSatDesc& dd, const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs,
-                          uint8_t* __restrict__ out, const uint32_t* tabL, const uint32_t* tabR, const int64_t* kL,
-                          const int64_t* kR) {
-  const MergeDesc& d = dd.m;
-  const int nt = 1 << d.tile_bits;
-  const int K = 1 << d.kbits;
-  const int64_t n_tiles = d.n_vec >> d.tile_bits;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint8_t* baseL = lhs + deposit(d.hiL, (uint64_t)tile);
-    const uint8_t* baseR = rhs + deposit(d.hiR, (uint64_t)tile);
-    uint4* outp = (uint4*)out + (tile << d.tile_bits);
-#pragma unroll 2
-    for (int vi = threadIdx.x; vi < nt; vi += kSatThreads) {
-      const uint8_t* pl = baseL + tabL[vi];
-      const uint8_t* pr = baseR + tabR[vi];
-      uint32_t a0, a1, a2, a3;
-      {
-        uint32_t XL[4], XR[4];
-        load_expand<NIBL, false>(pl, XL);
-        load_expand<NIBR, false>(pr, XR);
-        a0 = XL[0] & XR[0]; a1 = XL[1] & XR[1]; a2 = XL[2] & XR[2]; a3 = XL[3] & XR[3];
-      }
-      for (int kk = 1; kk < K; kk++) {
-        uint32_t XL[4], XR[4];
-        load_expand<NIBL, false>(pl + kL[kk], XL);
-        load_expand<NIBR, false>(pr + kR[kk], XR);
-        a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
-      }
-      if (d.accumulate) { uint4 p = outp[vi]; a0 |= p.x; a1 |= p.y; a2 |= p.z; a3 |= p.w; }
-      st_stream(outp + vi, make_uint4(a0, a1, a2, a3));
-    }
+template <int NIB>
+TSB_D void load_expand(const uint8_t* p, uint64_t pol, uint32_t X[4]) {
+  expand<NIB>(raw_load<NIB>(p, pol), X);
+}
+
+// Per-tile operand base: the tile-index bits are deposited run by run; one run per lane, OR-reduced
+// across the warp (every warp computes its own copy, no block barrier needed).
+struct RunsSmem {
+  uint32_t in_shift[32], out_shift[32];
+  uint64_t mask[32];
+};
+
+TSB_D void runs_to_smem(const BitRuns& r, RunsSmem& s) {
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+    const bool on = i < r.n;
+    s.in_shift[i] = on ? r.in_shift[i] : 0;
+    s.out_shift[i] = on ? r.out_shift[i] : 0;
+    s.mask[i] = on ? ((uint64_t(1) << r.len[i]) - 1) : 0;
   }
 }
 
+TSB_D uint64_t deposit_warp(const RunsSmem& s, uint64_t x) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t c = ((x >> s.in_shift[lane]) & s.mask[lane]) << s.out_shift[lane];
+  const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)c);
+  const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(c >> 32));
+  return ((uint64_t)hi << 32) | lo;
+}
+
 template <int NIBL, int NIBR>
-__global__ void __launch_bounds__(kSatThreads)
+__global__ void __launch_bounds__(kSatThreads, 2)
 k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs,
             uint8_t* __restrict__ out) {
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
   __shared__ int64_t kL[256], kR[256];
+  __shared__ RunsSmem runsL, runsR;
   const MergeDesc& d = dd.m;
   const int nt = 1 << d.tile_bits;
   for (int i = threadIdx.x; i < nt; i += kSatThreads) {
@@ -117,8 +170,85 @@ k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__
     kL[i] = a;
     kR[i] = b;
   }
+  runs_to_smem(d.hiL, runsL);
+  runs_to_smem(d.hiR, runsR);
   __syncthreads();
-  merge_sat_body<NIBL, NIBR>(dd, lhs, rhs, out, tabL, tabR, kL, kR);
+  const int K = 1 << d.kbits;
+  const int64_t k1L = d.kbits ? d.ksL[0] : 0, k1R = d.kbits ? d.ksR[0] : 0;
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const bool acc = d.accumulate != 0;
+  const uint64_t polL = l2_policy(dd.stream_l != 0), polR = l2_policy(dd.stream_r != 0), polO = l2_policy(true);
+  constexpr int G = 4;  // output vectors per thread (2 x 2 over bit_a, bit_b)
+  const int ba = dd.bit_a, bb = dd.bit_b;
+  const int nq = nt >> 2;
+  int64_t tile = blockIdx.x;
+  uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
+  uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
+  while (tile < n_tiles) {
+    const uint8_t* baseL = lhs + offL;
+    const uint8_t* baseR = rhs + offR;
+    uint4* outp = (uint4*)out + (tile << d.tile_bits);
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {  // bases of the next tile, off the critical path (uniform branch)
+      offL = deposit_warp(runsL, (uint64_t)next);
+      offR = deposit_warp(runsR, (uint64_t)next);
+    }
+    for (int i = threadIdx.x; i < nq; i += kSatThreads) {
+      // tile-local vector index with zeros inserted at bit_a and bit_b
+      const int lo = i & ((1 << ba) - 1);
+      const int mid = (i >> ba) & ((1 << (bb - ba - 1)) - 1);
+      const int hi = i >> (bb - 1);
+      const int v0 = lo | (mid << (ba + 1)) | (hi << (bb + 1));
+      int vi[G];
+      const uint8_t* pl[G];
+      const uint8_t* pr[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        vi[g] = v0 | ((g & 1) << ba) | ((g >> 1) << bb);
+        pl[g] = baseL + tabL[vi[g]];
+        pr[g] = baseR + tabR[vi[g]];
+      }
+      // an operand that does not depend on bit_a / bit_b yields equal addresses: load once (uniform branches)
+      const bool l1 = pl[1] != pl[0], l2 = pl[2] != pl[0];
+      const bool r1 = pr[1] != pr[0], r2 = pr[2] != pr[0];
+      Raw<NIBL> rl[G][2];
+      Raw<NIBR> rr[G][2];
+#pragma unroll
+      for (int kq = 0; kq < 2; kq++) {
+        if (kq == 1 && K < 2) break;
+        const int64_t oL = kq ? k1L : 0, oR = kq ? k1R : 0;
+        rl[0][kq] = raw_load<NIBL>(pl[0] + oL, polL);
+        rr[0][kq] = raw_load<NIBR>(pr[0] + oR, polR);
+        if (l1) rl[1][kq] = raw_load<NIBL>(pl[1] + oL, polL); else rl[1][kq] = rl[0][kq];
+        if (r1) rr[1][kq] = raw_load<NIBR>(pr[1] + oR, polR); else rr[1][kq] = rr[0][kq];
+        if (l2) rl[2][kq] = raw_load<NIBL>(pl[2] + oL, polL); else rl[2][kq] = rl[0][kq];
+        if (r2) rr[2][kq] = raw_load<NIBR>(pr[2] + oR, polR); else rr[2][kq] = rr[0][kq];
+        if (l1 && l2) rl[3][kq] = raw_load<NIBL>(pl[3] + oL, polL); else rl[3][kq] = l1 ? rl[1][kq] : rl[2][kq];
+        if (r1 && r2) rr[3][kq] = raw_load<NIBR>(pr[3] + oR, polR); else rr[3][kq] = r1 ? rr[1][kq] : rr[2][kq];
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        uint32_t XL[4], XR[4];
+        expand<NIBL>(rl[g][0], XL);
+        expand<NIBR>(rr[g][0], XR);
+        uint32_t a0 = XL[0] & XR[0], a1 = XL[1] & XR[1], a2 = XL[2] & XR[2], a3 = XL[3] & XR[3];
+        if (K >= 2) {
+          expand<NIBL>(rl[g][1], XL);
+          expand<NIBR>(rr[g][1], XR);
+          a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
+#pragma unroll 1
+          for (int kk = 2; kk < K; kk++) {
+            load_expand<NIBL>(pl[g] + kL[kk], polL, XL);
+            load_expand<NIBR>(pr[g] + kR[kk], polR, XR);
+            a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
+          }
+        }
+        if (acc) { uint4 p = outp[vi[g]]; a0 |= p.x; a1 |= p.y; a2 |= p.z; a3 |= p.w; }
+        stg_hint_v4(outp + vi[g], make_uint4(a0, a1, a2, a3), polO);
+      }
+    }
+    tile = next;
+  }
 }
 
 // Preconditions checked by the host: has_rhs, kbits <= 8, table offsets < 2^32.

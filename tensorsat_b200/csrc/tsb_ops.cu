@@ -1,4 +1,6 @@
 // tsb_ops.cu — C-ABI entry points for contexts, the arena and the single box operations.
+#include <cmath>
+
 #include "lower.h"
 
 namespace tsb {
@@ -50,6 +52,48 @@ static int64_t numel(const int32_t* ext, int rank) {
   int64_t n = 1;
   for (int i = 0; i < rank; i++) n *= ext[i];
   return n;
+}
+
+#ifndef TSB_HOST_EMU
+void gemm_u8_impl(tsb_ctx* ctx, const void* A, const void* B, void* C, int b_bits, int m_bits, int n_bits, int k_bits,
+                  int out_dtype, int mode, cudaStream_t stream);
+#endif
+
+// Label classes of a pairwise step over bit labels, and whether the step is worth the tensor cores:
+// arithmetic intensity above `min_intensity` op/B and a tile the UMMA shape can fill.
+struct GemmShape {
+  bool ok = false;
+  bool swap = false;  // use rhs as the M side
+  BitLabels B, M, N, K;
+};
+
+GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& ob, int out_elem_size,
+                     double min_intensity) {
+  GemmShape g;
+  std::set<int64_t> sl(lb.begin(), lb.end()), sr(rb.begin(), rb.end()), so(ob.begin(), ob.end());
+  for (auto x : ob) {
+    const bool inl = sl.count(x) != 0, inr = sr.count(x) != 0;
+    if (inl && inr) g.B.push_back(x);
+    else if (inl) g.M.push_back(x);
+    else if (inr) g.N.push_back(x);
+    else return g;
+  }
+  for (auto x : lb)
+    if (!so.count(x)) {
+      if (!sr.count(x)) return g;  // lone label: not a plain GEMM
+      g.K.push_back(x);
+    }
+  for (auto x : rb)
+    if (!so.count(x) && !sl.count(x)) return g;
+  int m = (int)g.M.size(), n = (int)g.N.size();
+  const int k = (int)g.K.size(), b = (int)g.B.size();
+  if (m < n) { std::swap(g.M, g.N); std::swap(m, n); g.swap = true; }
+  if (m < 7 || n < 5 || k < 5 || k > 15) return g;
+  const double ops = 2.0 * std::exp2((double)(b + m + n + k));
+  const double bytes = std::exp2((double)(b + m + k)) + std::exp2((double)(b + n + k)) +
+                       out_elem_size * std::exp2((double)(b + m + n));
+  g.ok = ops / bytes >= min_intensity;
+  return g;
 }
 
 // Generic-kernel descriptor of an einsum-like pairwise step (any extents, repeated / dropped labels).
@@ -117,6 +161,59 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
     BitLabels lb = bit_labels(lhs_wires, lhs_rank, wext), rb = bit_labels(rhs_wires, rhs_rank, wext),
               ob = bit_labels(out_wires, out_rank, wext);
     if (has_dups(lb) || has_dups(rb) || has_dups(ob)) fast = false;
+#ifndef TSB_HOST_EMU
+    // ---- tensor cores: steps above the ridge go through transpose -> int8 GEMM -> transpose
+    if (fast && !accumulate && dl == TSB_U8 && dr == TSB_U8 && (clamp ? dout == TSB_U8 : dout != TSB_U8)) {
+      GemmShape g = gemm_shape(lb, rb, ob, dtype_size(dout), 64.0);
+      if (g.ok) {
+        const void* pa = g.swap ? rhs : lhs;
+        const void* pb = g.swap ? lhs : rhs;
+        const BitLabels& ab = g.swap ? rb : lb;
+        const BitLabels& bb = g.swap ? lb : rb;
+        auto cat = [](const BitLabels& x, const BitLabels& y, const BitLabels& z) {
+          BitLabels r = x; r.insert(r.end(), y.begin(), y.end()); r.insert(r.end(), z.begin(), z.end()); return r;
+        };
+        const BitLabels a_can = cat(g.B, g.M, g.K), b_can = cat(g.B, g.N, g.K), c_can = cat(g.B, g.M, g.N);
+        std::unique_ptr<Temp> ta, tb, tc, tc2;
+        if (ab != a_can) {
+          ta.reset(new Temp(ctx, (size_t)1 << ab.size()));
+          permute_bits(ctx, pa, ab, ta->p, a_can, 1, stream);
+          pa = ta->p;
+        }
+        if (bb != b_can) {
+          tb.reset(new Temp(ctx, (size_t)1 << bb.size()));
+          permute_bits(ctx, pb, bb, tb->p, b_can, 1, stream);
+          pb = tb->p;
+        }
+        const int gemm_dt = clamp ? TSB_U8 : TSB_I32;
+        void* pc = out;
+        if (c_can != ob || gemm_dt != dout) {
+          tc.reset(new Temp(ctx, (size_t)dtype_size(gemm_dt) << ob.size()));
+          pc = tc->p;
+        }
+        gemm_u8_impl(ctx, pa, pb, pc, (int)g.B.size(), (int)g.M.size(), (int)g.N.size(), (int)g.K.size(), gemm_dt,
+                     mode, stream);
+        if (pc != out) {
+          void* src = pc;
+          if (gemm_dt != dout) {  // counting mode with an int64 result: widen after the transpose-free case
+            if (c_can == ob) {
+              TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n_out, 256)), dim3(256), 0, stream, (const void*)src, gemm_dt, out,
+                         dout, n_out, 0);
+              ctx->launches++;
+              return;
+            }
+            tc2.reset(new Temp(ctx, (size_t)dtype_size(dout) << ob.size()));
+            TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n_out, 256)), dim3(256), 0, stream, (const void*)src, gemm_dt,
+                       tc2->p, dout, n_out, 0);
+            ctx->launches++;
+            src = tc2->p;
+          }
+          permute_bits(ctx, src, c_can, out, ob, dtype_size(dout), stream);
+        }
+        return;
+      }
+    }
+#endif
     if (fast) {
       MergeArgs m = make_merge_desc(lb, &rb, ob, accumulate);
       std::unique_ptr<Temp> tl, tr;

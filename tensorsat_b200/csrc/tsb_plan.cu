@@ -27,6 +27,12 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
 void rewire_impl(tsb_ctx* ctx, const void* src, int src_rank, const int32_t* sext, const int32_t* fixed_idx, int ds,
                  void* dst, int out_rank, const int32_t* out_ports, int dd, bool clamp, bool accumulate,
                  cudaStream_t stream);
+struct GemmShape {
+  bool ok = false;
+  bool swap = false;
+  BitLabels B, M, N, K;
+};
+GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& ob, int out_elem_size, double min_intensity);
 GenDesc lower_generic_contract(int lhs_rank, const int32_t* lhs_wires, int rhs_rank, const int32_t* rhs_wires,
                                int out_rank, const int32_t* out_wires, const int32_t* wext, int dl, int dr, int dout,
                                bool clamp, bool accumulate, bool& out_dups);
@@ -59,6 +65,7 @@ struct POp {
   bool per_slice = false;
   int lhs = -1, rhs = -1, out = -1;  // node ids
   bool use_merge = false;
+  bool use_gemm = false;  // lowered at run time: transposes + tcgen05 int8 GEMM
   MergeDesc md{};
   // generic description (wires + extents) used when the merge kernel does not apply
   std::vector<int32_t> lw, rw, ow;
@@ -427,14 +434,23 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
         BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
         BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
+        bool to_gemm = false;
+#ifndef TSB_HOST_EMU
+        // steps above the ridge are lowered at run time by contract2_impl (transpose -> tcgen05 GEMM -> transpose)
+        if (!(P.flags & TSB_PLAN_NO_GEMM) && P.nodes[op.lhs].dtype == TSB_U8 && P.nodes[op.rhs].dtype == TSB_U8 &&
+            (clamp ? o.dtype == TSB_U8 : o.dtype != TSB_U8) && !(op.per_slice && op.out == P.root))
+          to_gemm = gemm_shape(lb, rb, ob, dtype_size(o.dtype), 64.0).ok;
+#endif
         MergeArgs m = make_merge_desc(lb, &rb, ob, false);
-        if (m.ok) {
+        if (to_gemm) {
+          op.use_gemm = true;
+        } else if (m.ok) {
           op.use_merge = true;
           op.md = m.d;
         }
       }
     }
-    if (op.use_merge) continue;
+    if (op.use_merge || op.use_gemm) continue;
     // generic kernel: lowered once, here (the root of a sliced plan accumulates and stays on the slow path)
     if (op.kind == OP_LEAF) {
       const auto& lw = P.leaf_wires[op.leaf];
@@ -743,7 +759,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     if (!first) os << ",";
     first = false;
     const PNode& o = plan->nodes[op.out];
-    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_STEP ? (op.use_merge ? "merge" : "generic") : "permute")
+    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_STEP ? (op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
        << ",\"small\":" << (op.small ? 1 : 0) << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
