@@ -17,9 +17,7 @@ constexpr int kSatThreads = 256;
 struct MergeSatDesc {
   MergeDesc m;
   int32_t stream_l, stream_r;  // operand bytes are used once: load with evict-first
-  // A thread computes the 4 output vectors whose tile-local index differs in bits bit_a < bit_b; the host
-  // picks bits one operand does not depend on, so that operand's vector is loaded once for 2 (or 4) outputs.
-  int32_t bit_a, bit_b;
+  int32_t bit_a, bit_b;        // reserved (register tiling over operand-independent bits: measured slower)
 };
 
 constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1) + ((x >> 2) & 1) + ((x >> 3) & 1); }
@@ -151,7 +149,7 @@ TSB_D uint64_t deposit_warp(const RunsSmem& s, uint64_t x) {
 }
 
 template <int NIBL, int NIBR>
-__global__ void __launch_bounds__(kSatThreads, 2)
+__global__ void __launch_bounds__(kSatThreads, 4)
 k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs,
             uint8_t* __restrict__ out) {
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
@@ -178,9 +176,7 @@ k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const bool acc = d.accumulate != 0;
   const uint64_t polL = l2_policy(dd.stream_l != 0), polR = l2_policy(dd.stream_r != 0), polO = l2_policy(true);
-  constexpr int G = 4;  // output vectors per thread (2 x 2 over bit_a, bit_b)
-  const int ba = dd.bit_a, bb = dd.bit_b;
-  const int nq = nt >> 2;
+  constexpr int G = 2;  // vectors per thread whose loads are all issued before any is consumed
   int64_t tile = blockIdx.x;
   uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
   uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
@@ -193,58 +189,47 @@ k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__
       offL = deposit_warp(runsL, (uint64_t)next);
       offR = deposit_warp(runsR, (uint64_t)next);
     }
-    for (int i = threadIdx.x; i < nq; i += kSatThreads) {
-      // tile-local vector index with zeros inserted at bit_a and bit_b
-      const int lo = i & ((1 << ba) - 1);
-      const int mid = (i >> ba) & ((1 << (bb - ba - 1)) - 1);
-      const int hi = i >> (bb - 1);
-      const int v0 = lo | (mid << (ba + 1)) | (hi << (bb + 1));
-      int vi[G];
+    for (int v0 = threadIdx.x; v0 < nt; v0 += kSatThreads * G) {
+      Raw<NIBL> rl[G][2];
+      Raw<NIBR> rr[G][2];
       const uint8_t* pl[G];
       const uint8_t* pr[G];
 #pragma unroll
       for (int g = 0; g < G; g++) {
-        vi[g] = v0 | ((g & 1) << ba) | ((g >> 1) << bb);
-        pl[g] = baseL + tabL[vi[g]];
-        pr[g] = baseR + tabR[vi[g]];
-      }
-      // an operand that does not depend on bit_a / bit_b yields equal addresses: load once (uniform branches)
-      const bool l1 = pl[1] != pl[0], l2 = pl[2] != pl[0];
-      const bool r1 = pr[1] != pr[0], r2 = pr[2] != pr[0];
-      Raw<NIBL> rl[G][2];
-      Raw<NIBR> rr[G][2];
-#pragma unroll
-      for (int kq = 0; kq < 2; kq++) {
-        if (kq == 1 && K < 2) break;
-        const int64_t oL = kq ? k1L : 0, oR = kq ? k1R : 0;
-        rl[0][kq] = raw_load<NIBL>(pl[0] + oL, polL);
-        rr[0][kq] = raw_load<NIBR>(pr[0] + oR, polR);
-        if (l1) rl[1][kq] = raw_load<NIBL>(pl[1] + oL, polL); else rl[1][kq] = rl[0][kq];
-        if (r1) rr[1][kq] = raw_load<NIBR>(pr[1] + oR, polR); else rr[1][kq] = rr[0][kq];
-        if (l2) rl[2][kq] = raw_load<NIBL>(pl[2] + oL, polL); else rl[2][kq] = rl[0][kq];
-        if (r2) rr[2][kq] = raw_load<NIBR>(pr[2] + oR, polR); else rr[2][kq] = rr[0][kq];
-        if (l1 && l2) rl[3][kq] = raw_load<NIBL>(pl[3] + oL, polL); else rl[3][kq] = l1 ? rl[1][kq] : rl[2][kq];
-        if (r1 && r2) rr[3][kq] = raw_load<NIBR>(pr[3] + oR, polR); else rr[3][kq] = r1 ? rr[1][kq] : rr[2][kq];
+        const int vi = v0 + g * kSatThreads;
+        if (vi < nt) {
+          pl[g] = baseL + tabL[vi];
+          pr[g] = baseR + tabR[vi];
+          rl[g][0] = raw_load<NIBL>(pl[g], polL);
+          rr[g][0] = raw_load<NIBR>(pr[g], polR);
+          if (K >= 2) {
+            rl[g][1] = raw_load<NIBL>(pl[g] + k1L, polL);
+            rr[g][1] = raw_load<NIBR>(pr[g] + k1R, polR);
+          }
+        }
       }
 #pragma unroll
       for (int g = 0; g < G; g++) {
-        uint32_t XL[4], XR[4];
-        expand<NIBL>(rl[g][0], XL);
-        expand<NIBR>(rr[g][0], XR);
-        uint32_t a0 = XL[0] & XR[0], a1 = XL[1] & XR[1], a2 = XL[2] & XR[2], a3 = XL[3] & XR[3];
-        if (K >= 2) {
-          expand<NIBL>(rl[g][1], XL);
-          expand<NIBR>(rr[g][1], XR);
-          a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
-#pragma unroll 1
-          for (int kk = 2; kk < K; kk++) {
-            load_expand<NIBL>(pl[g] + kL[kk], polL, XL);
-            load_expand<NIBR>(pr[g] + kR[kk], polR, XR);
+        const int vi = v0 + g * kSatThreads;
+        if (vi < nt) {
+          uint32_t XL[4], XR[4];
+          expand<NIBL>(rl[g][0], XL);
+          expand<NIBR>(rr[g][0], XR);
+          uint32_t a0 = XL[0] & XR[0], a1 = XL[1] & XR[1], a2 = XL[2] & XR[2], a3 = XL[3] & XR[3];
+          if (K >= 2) {
+            expand<NIBL>(rl[g][1], XL);
+            expand<NIBR>(rr[g][1], XR);
             a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
+#pragma unroll 1
+            for (int kk = 2; kk < K; kk++) {
+              load_expand<NIBL>(pl[g] + kL[kk], polL, XL);
+              load_expand<NIBR>(pr[g] + kR[kk], polR, XR);
+              a0 |= XL[0] & XR[0]; a1 |= XL[1] & XR[1]; a2 |= XL[2] & XR[2]; a3 |= XL[3] & XR[3];
+            }
           }
+          if (acc) { uint4 p = outp[vi]; a0 |= p.x; a1 |= p.y; a2 |= p.z; a3 |= p.w; }
+          stg_hint_v4(outp + vi, make_uint4(a0, a1, a2, a3), polO);
         }
-        if (acc) { uint4 p = outp[vi[g]]; a0 |= p.x; a1 |= p.y; a2 |= p.z; a3 |= p.w; }
-        stg_hint_v4(outp + vi[g], make_uint4(a0, a1, a2, a3), polO);
       }
     }
     tile = next;
