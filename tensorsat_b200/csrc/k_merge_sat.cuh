@@ -124,30 +124,6 @@ TSB_D void load_expand(const uint8_t* p, uint64_t pol, uint32_t X[4]) {
   expand<NIB>(raw_load<NIB>(p, pol), X);
 }
 
-// Per-tile operand base: the tile-index bits are deposited run by run; one run per lane, OR-reduced
-// across the warp (every warp computes its own copy, no block barrier needed).
-struct RunsSmem {
-  uint32_t in_shift[32], out_shift[32];
-  uint64_t mask[32];
-};
-
-TSB_D void runs_to_smem(const BitRuns& r, RunsSmem& s) {
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-    const bool on = i < r.n;
-    s.in_shift[i] = on ? r.in_shift[i] : 0;
-    s.out_shift[i] = on ? r.out_shift[i] : 0;
-    s.mask[i] = on ? ((uint64_t(1) << r.len[i]) - 1) : 0;
-  }
-}
-
-TSB_D uint64_t deposit_warp(const RunsSmem& s, uint64_t x) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t c = ((x >> s.in_shift[lane]) & s.mask[lane]) << s.out_shift[lane];
-  const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)c);
-  const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(c >> 32));
-  return ((uint64_t)hi << 32) | lo;
-}
-
 template <int NIBL, int NIBR>
 __global__ void __launch_bounds__(kSatThreads, 4)
 k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs,

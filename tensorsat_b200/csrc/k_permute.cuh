@@ -59,11 +59,21 @@ k_permute(const __grid_constant__ PermDesc d, const uint8_t* __restrict__ src, u
   uint32_t off[16 / G];
 #pragma unroll
   for (int e = 0; e < 16 / G; e++) off[e] = perm_swz((uint32_t)deposit(d.d2s, (uint64_t)(e * G)), lo);
+  __shared__ RunsSmem runs_s, runs_d;
+  runs_to_smem(d.cta_src, runs_s);
+  runs_to_smem(d.cta_dst, runs_d);
   __syncthreads();
   const uint32_t amask = (1u << d.a_bits) - 1u, bmask = (1u << d.b_bits) - 1u;
-  for (int64_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
-    const uint8_t* s0 = src + deposit(d.cta_src, (uint64_t)tile);
-    uint8_t* d0 = dst + deposit(d.cta_dst, (uint64_t)tile);
+  int64_t tile = blockIdx.x;
+  uint64_t off_s = tile < d.n_tiles ? deposit_warp(runs_s, (uint64_t)tile) : 0;
+  uint64_t off_d = tile < d.n_tiles ? deposit_warp(runs_d, (uint64_t)tile) : 0;
+  for (; tile < d.n_tiles; tile += gridDim.x) {
+    const uint8_t* s0 = src + off_s;
+    uint8_t* d0 = dst + off_d;
+    if (tile + gridDim.x < d.n_tiles) {  // next tile's offsets, one bit run per lane (uniform branch)
+      off_s = deposit_warp(runs_s, (uint64_t)(tile + gridDim.x));
+      off_d = deposit_warp(runs_d, (uint64_t)(tile + gridDim.x));
+    }
     // ---- load phase: tile-src order, 16-byte vectors, swizzled into shared memory
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
       const uint32_t js = (uint32_t)v << 4;

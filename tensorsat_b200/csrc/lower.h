@@ -246,7 +246,7 @@ inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits,
   int g = 0;
   while (g < 4 && g < r && s[g] == t[g]) g++;
   G = 1 << g;
-  const int tb = std::min(r, 13);
+  const int tb = std::min(r, 14);
   const int a = std::min(7, r), b = std::min(7, r);
   std::set<int64_t> T;
   for (int i = 0; i < a; i++) T.insert(s[i]);
@@ -278,6 +278,7 @@ inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits,
     runs_add(cs, ci, spos[t[i]]);
     ci++;
   }
+  if (cs.n > 32 || cd.n > 32) return false;  // one run per lane in the kernel
   d.cta_src = cs; d.cta_dst = cd;
   d.n_tiles = int64_t(1) << (r - tbits);
   return true;
@@ -454,10 +455,25 @@ void launch_merge_sat(tsb_ctx* ctx, const MergeDesc& d, const void* l, const voi
 void launch_merge_generic(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
                           int dout, bool clamp, cudaStream_t s);
 
+template <typename TL, typename TR>
+void launch_merge_cnt_t(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, cudaStream_t stream);
+template <> void launch_merge_cnt_t<uint8_t, uint8_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
+template <> void launch_merge_cnt_t<uint8_t, int32_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
+template <> void launch_merge_cnt_t<int32_t, uint8_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
+template <> void launch_merge_cnt_t<int32_t, int32_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
+
 inline void launch_merge(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
                          int dout, bool clamp, cudaStream_t s) {
   if (clamp && dl == TSB_U8 && dr == TSB_U8 && dout == TSB_U8 && merge_sat_supported(d)) {
     launch_merge_sat(ctx, d, l, r, o, s);
+    return;
+  }
+  if (!clamp && dout == TSB_I32 && dl != TSB_I64 && dr != TSB_I64 && merge_sat_supported(d)) {
+    // counting semiring, int32 results: compile-time specialised kernel
+    if (dl == TSB_U8 && dr == TSB_U8) launch_merge_cnt_t<uint8_t, uint8_t>(ctx, d, l, r, o, s);
+    else if (dl == TSB_U8) launch_merge_cnt_t<uint8_t, int32_t>(ctx, d, l, r, o, s);
+    else if (dr == TSB_U8) launch_merge_cnt_t<int32_t, uint8_t>(ctx, d, l, r, o, s);
+    else launch_merge_cnt_t<int32_t, int32_t>(ctx, d, l, r, o, s);
     return;
   }
   launch_merge_generic(ctx, d, l, dl, r, dr, o, dout, clamp, s);

@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "tensorsat_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libtsb_emu.so")
-SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu", "tsb_merge_sat.cu", "tsb_merge_gen.cu"]
+SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu", "tsb_merge_sat.cu", "tsb_merge_gen.cu",
+           "tsb_merge_cnt_88.cu", "tsb_merge_cnt_84.cu", "tsb_merge_cnt_48.cu", "tsb_merge_cnt_44.cu"]
 
 
 def build(force: bool = False) -> str:
@@ -25,13 +26,16 @@ def build(force: bool = False) -> str:
     deps.append(os.path.join(ROOT, "include", "tsb.h"))
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps if os.path.isfile(d)):
         return LIB
-    objs = []
+    objs, procs = [], []
     for s in SOURCES:
         obj = os.path.join(OUT, s[:-3] + ".o")
-        subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-DTSB_HOST_EMU", "-x", "c++", "-c",
-                        os.path.join(CSRC, s), "-o", obj, "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
-                        "-Wno-sign-compare"], check=True)
+        procs.append(subprocess.Popen(["g++", "-O1", "-std=c++17", "-fPIC", "-DTSB_HOST_EMU", "-x", "c++", "-c",
+                                       os.path.join(CSRC, s), "-o", obj, "-Wall", "-Wno-unused-function",
+                                       "-Wno-unknown-pragmas", "-Wno-sign-compare"]))
         objs.append(obj)
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("g++ failed")
     subprocess.run(["g++", "-shared", "-o", LIB, *objs], check=True)
     return LIB
 

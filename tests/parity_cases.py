@@ -163,6 +163,32 @@ def test_contract2_ordered_big():
     assert np.array_equal(gotc.tensor, O.contract2(big, big_w, small, small_w, ow, mode="count"))
 
 
+@pytest.mark.parametrize("tl,tr", [("u8", "u8"), ("u8", "i32"), ("i32", "u8"), ("i32", "i32")])
+def test_counting_merge_int32_kernels(tl, tr):
+    """The compile-time specialised counting kernels (int32 results) through tsb_contract2, all operand type pairs."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(11)
+    dt = {"u8": (np.uint8, torch.uint8, 4), "i32": (np.int32, torch.int32, 3000)}
+    for trial in range(6):
+        R = int(rng.integers(12, SCALE["big_bits"] - 1))
+        out_w = list(range(2, R + 2))                       # wires 0, 1 are summed; all wires in one global order
+        lw = [0, 1] + sorted(int(w) for w in rng.choice(out_w, size=int(rng.integers(2, R)), replace=False))
+        rest = [w for w in out_w if w not in lw]
+        rw = [0] + ([1] if trial % 2 else []) + sorted(set(rest) | set(int(w) for w in rng.choice(out_w, size=int(rng.integers(1, R)), replace=False)))
+        L = rng.integers(0, dt[tl][2], size=(2,) * len(lw)).astype(dt[tl][0])
+        Rr = rng.integers(0, dt[tr][2], size=(2,) * len(rw)).astype(dt[tr][0])
+        dev = _native.device()
+        Ld, Rd = torch.from_numpy(L.reshape(-1)).to(dev), torch.from_numpy(Rr.reshape(-1)).to(dev)
+        Od = torch.empty(1 << R, dtype=torch.int32, device=dev)
+        _native.contract2(Ld, [2] * len(lw), lw, Rd, [2] * len(rw), rw, Od, [2] * R, out_w, 1)
+        want = O.einsum2(L.astype(np.int64), lw, Rr.astype(np.int64), rw, out_w)
+        assert want.max() < 2**31
+        assert np.array_equal(Od.cpu().numpy().reshape((2,) * R).astype(np.int64), want)
+
+
 def test_contract2_validation_errors():
     a, b = CudaFinRel(np.ones((2, 2), np.uint8)), CudaFinRel(np.ones((2,), np.uint8))
     with pytest.raises(ValueError):

@@ -20,16 +20,21 @@ def main():
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--batch-log2", type=int, default=-1)
     ap.add_argument("--json", default="")
+    ap.add_argument("--count", action="store_true", help="counting semiring (#SAT) instead of SAT")
     args = ap.parse_args()
     import torch
 
     import bench
     from tensorsat_b200 import _native
     from tensorsat_b200.contractions.tree import TreeContraction
-    from tensorsat_b200.lang.fin_rel import CudaFinRel
+    from tensorsat_b200.lang.fin_rel import CudaCountRel, CudaFinRel
 
     cnf, diagram, tree = bench.load_tree()
-    c = TreeContraction(CudaFinRel, diagram.wiring, tree=tree, batch_log2=args.batch_log2)
+    if args.count:
+        c = TreeContraction(CudaCountRel, diagram.wiring, tree=tree, batch_log2=args.batch_log2,
+                            wire_is_free=[w < cnf.num_vars for w in diagram.wiring.wires])
+    else:
+        c = TreeContraction(CudaFinRel, diagram.wiring, tree=tree, batch_log2=args.batch_log2)
     plan = c.plan()
     hi = plan.info["n_slices"] if args.slices <= 0 else min(args.slices, plan.info["n_slices"])
     leaves = [c._leaf_tensor(b) for b in diagram.boxes]
@@ -55,7 +60,7 @@ def main():
         k["n"] += mult
         k["ms"] += o["ms"]
         k["bytes"] += o["bytes"] * mult
-    print(f"untimed execution: {total_ms:.3f} ms for {hi} slice(s); info={plan.info}")
+    print(f"untimed execution: {total_ms:.3f} ms for {hi} slice(s); result={out.cpu().numpy().reshape(-1)[:4]} info={plan.info}")
     for (kind, ps), k in sorted(kinds.items()):
         gbps = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else 0
         print(f"{kind:8s} per_slice={ps} launches={k['n']:6d} ms={k['ms']:9.3f} alg_GB={k['bytes']/1e9:9.3f} GB/s={gbps:8.1f}")
@@ -63,7 +68,7 @@ def main():
     for o in ops_sorted:
         mult = hi if o["per_slice"] else 1
         gbps = o["bytes"] * mult / (o["ms"] * 1e-3) / 1e9 if o["ms"] else 0
-        print(f"{o['kind']:8s} ps={o['per_slice']} out_bits={o['out_bits']:2d} b={o['b']:2d} m={o['m']:2d} n={o['n']:2d} k={o['k']} "
+        print(f"{o['kind']:8s} ps={o['per_slice']} dt={o['dtype']} out_bits={o['out_bits']:2d} b={o['b']:2d} m={o['m']:2d} n={o['n']:2d} k={o['k']} "
               f"ms(total over slices)={o['ms']:8.3f} per-launch us={o['ms']/mult*1e3:9.1f} GB/s={gbps:8.1f}")
     if args.json:
         with open(args.json, "w") as f:
