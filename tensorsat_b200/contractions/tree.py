@@ -57,9 +57,11 @@ class TreeContraction(Contraction):
         for t in wiring.wire_types:
             if not isinstance(t, TensorLikeType):
                 raise ValueError("Wiring must have tensor-like wire types.")
-        if len(set(wiring.out_wires)) != len(wiring.out_wires):
-            raise NotImplementedError("Repeated output wires: contract onto distinct wires, then rewire.")
         net = Network.from_wiring(wiring)
+        # repeated output wires: contract onto the distinct wires, then rewire (simple.py:287-289 does the same)
+        self._distinct_out = tuple(dict.fromkeys(wiring.out_wires))
+        if len(self._distinct_out) != len(wiring.out_wires):
+            net = Network(net.inputs, self._distinct_out, net.size_dict)
         if tree is not None:
             if tree.network != net:
                 raise ValueError("The tree was built for a different wiring.")
@@ -185,8 +187,11 @@ class TreeContraction(Contraction):
         Keyword arguments of the reference (``order``, ``autojit``, ``progbar``) are accepted and ignored.
         """
         out = self.contract_raw(diagram, slice_range)
-        dims = tuple(self.wiring.wire_dims[w] for w in self.wiring.out_wires)
-        return self.box_class._new(dims, dev=out)
+        dims = tuple(self.wiring.wire_dims[w] for w in self._distinct_out)
+        box = self.box_class._new(dims, dev=out)
+        if self._distinct_out != tuple(self.wiring.out_wires):
+            box = box._rewire([self._distinct_out.index(w) for w in self.wiring.out_wires])
+        return box
 
     def __repr__(self) -> str:
         return "<TreeContraction>"

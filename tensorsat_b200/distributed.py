@@ -50,5 +50,8 @@ def contract_distributed(contraction: TreeContraction, diagram: Diagram, group: 
     lo, hi = slice_block(contraction.num_slices, rank, world)
     out = contraction.contract_raw(diagram, (lo, hi))
     all_reduce_result(out, contraction.mode, group)
-    dims = tuple(contraction.wiring.wire_dims[w] for w in contraction.wiring.out_wires)
-    return contraction.box_class._new(dims, dev=out)
+    dims = tuple(contraction.wiring.wire_dims[w] for w in contraction._distinct_out)
+    box = contraction.box_class._new(dims, dev=out)
+    if contraction._distinct_out != tuple(contraction.wiring.out_wires):
+        box = box._rewire([contraction._distinct_out.index(w) for w in contraction.wiring.out_wires])
+    return box

@@ -256,6 +256,8 @@ class _CudaTensorBox(TensorLikeBox):
     ) -> Self:
         from .. import _native
 
+        if type(lhs) is not type(rhs) or not hasattr(cls, "_MODE") or not isinstance(lhs, cls):
+            raise TypeError("Operands must be boxes of the same semiring (CudaFinRel or CudaCountRel).")
         ldev, ldims, lw = lhs._physical_wires(lhs_wires)
         rdev, rdims, rw = rhs._physical_wires(rhs_wires)
         dim_of: dict[int, int] = {}

@@ -392,3 +392,90 @@ def test_arena_is_reused_across_executions():
     assert after["device_allocs"] == before["device_allocs"]
     assert after["cache_hits"] >= before["cache_hits"] + 3
     assert after["in_use_bytes"] == before["in_use_bytes"]
+
+
+# ------------------------------------------------------------------------------------ autoray backend
+def test_autoray_backend_functions():
+    """einsum / tensordot / transpose / reshape / stack / shape with the reference's signatures (_autoray.py:31-80)."""
+    from tensorsat_b200 import autoray_backend as ab
+
+    rng = np.random.default_rng(3)
+    a, b = _rand01(rng, (2, 2, 2, 2)), _rand01(rng, (2, 2, 2))
+    A, B = CudaFinRel(a), CudaFinRel(b)
+    assert ab.shape(A) == (2, 2, 2, 2)
+    assert np.array_equal(ab.einsum("abcd,cde->abe", A, B).tensor, np.sign(np.einsum("abcd,cde->abe", a, b)).astype(np.uint8))
+    assert np.array_equal(ab.einsum("abcd->ca", A).tensor, np.sign(np.einsum("abcd->ca", a.astype(np.int64))).astype(np.uint8))
+    got = ab.tensordot(A, B, axes=([2, 3], [0, 1]))
+    assert np.array_equal(got.tensor, np.sign(np.tensordot(a.astype(np.int64), b, axes=([2, 3], [0, 1]))).astype(np.uint8))
+    got = ab.tensordot(A, B, axes=1)
+    assert np.array_equal(got.tensor, np.sign(np.tensordot(a.astype(np.int64), b, axes=1)).astype(np.uint8))
+    assert np.array_equal(ab.transpose(A, (3, 1, 0, 2)).tensor, np.transpose(a, (3, 1, 0, 2)))
+    assert np.array_equal(ab.transpose(B).tensor, np.transpose(b))
+    assert np.array_equal(ab.reshape(ab.transpose(A, (1, 0, 2, 3)), (4, 4)).tensor, np.transpose(a, (1, 0, 2, 3)).reshape(4, 4))
+    assert np.array_equal(ab.reshape(A, (-1, 2)).tensor, a.reshape(-1, 2))
+    assert np.array_equal(ab.stack([B, B, B], 1).tensor, np.stack([b, b, b], 1))
+    C = CudaCountRel(a)
+    assert np.array_equal(ab.tensordot(C, C, axes=2).tensor, np.tensordot(a.astype(np.int64), a.astype(np.int64), axes=2))
+    with pytest.raises(TypeError):
+        ab.shape(3)
+    with pytest.raises(ValueError):
+        ab.reshape(A, (3, 5))
+    with pytest.raises(TypeError):
+        ab.einsum("ab,bc->ac", CudaFinRel(a[0, 0]), CudaCountRel(a[0, 0]))
+
+
+def test_box_protocol_misc():
+    """prod / union / spider validation / equality / hash / inspectors (diagrams.py:719-996, fin_rel.py:395-493)."""
+    xor_, and_, bit = bc.xor_, bc.and_, bc.bit
+    p = CudaFinRel.prod([bc.bit_0, bc.bit_1, bc.bit_unk])           # G10
+    assert p.to_set() == {(0, 1, 0), (0, 1, 1)}
+    assert CudaFinRel.union([and_, xor_]).to_set() == and_.to_set() | xor_.to_set()
+    assert xor_.rewire([0, 2, 1]) == xor_ and hash(xor_.rewire([0, 2, 1])) == hash(xor_)
+    assert xor_.is_function_graph([0, 1]) and xor_.to_mapping([0, 1])[(1, 0)] == (1,)
+    assert not bc.bit_unk.is_function_graph([])
+    with pytest.raises(ValueError):
+        CudaFinRel.spider(bit, 0)
+    with pytest.raises(ValueError):
+        CudaFinRel.union([])
+    with pytest.raises(ValueError):
+        CudaFinRel.union([and_, bc.not_])
+    with pytest.raises(ValueError):
+        CudaFinRel.stack([and_], 4)
+    with pytest.raises(TypeError):
+        CudaFinRel.prod([and_, CudaCountRel.from_rel(and_)])
+    trit = FinSet(3)
+    sp = CudaFinRel.spider(trit, 2)
+    assert sp.tensor_shape == (3, 3) and sp.to_set() == {(0, 0), (1, 1), (2, 2)}
+    with pytest.raises(TypeError):
+        type("Sub", (CudaFinRel,), {})
+
+
+def test_factoring_with_the_wallace_multiplier():
+    """BASELINE config 5 at a contractible size: fix the product bits of a 3x3 / 4x4 Wallace multiplier and
+    read the factor pairs off the relation over the input bits."""
+    from tensorsat_b200.diagrams import DiagramBuilder
+
+    for nbits, N in ((3, 35), (4, 143), (4, 165)):
+        mult = bc.wallace_multiplier(nbits)
+        n_out = mult.num_ports - 2 * nbits
+        builder = DiagramBuilder()
+        ins = builder.add_inputs(bc.bits(2 * nbits))
+        outs = mult @ builder[ins]
+        for i, w in enumerate(outs):
+            ((bc.bit_1 if (N >> i) & 1 else bc.bit_0) @ builder[w])
+        d = builder.diagram().flatten()
+        res = TreeContraction(CudaFinRel, d.wiring, trials=2).contract(d)
+        if nbits == 3:  # repeated output wires: contracted onto distinct wires, then rewired
+            builder.add_outputs(ins[:2])
+            d2 = builder.diagram().flatten()
+            res2 = TreeContraction(CudaFinRel, d2.wiring, trials=2).contract(d2)
+            assert res2.to_set() == {pt + pt[:2] for pt in res.to_set()}
+        pairs = set()
+        for pt in res.to_set():
+            a = sum(b << i for i, b in enumerate(pt[:nbits]))
+            b_ = sum(b << i for i, b in enumerate(pt[nbits:]))
+            pairs.add((a, b_))
+        want = {(a, b_) for a in range(1 << nbits) for b_ in range(1 << nbits) if a * b_ == N}
+        assert pairs == want and want, (nbits, N, n_out)
+        cnt = TreeContraction(CudaCountRel, d.wiring, trials=2, wire_is_free=[w < 2 * nbits for w in d.wiring.wires]).contract(d)
+        assert int(cnt.tensor.sum()) == len(want)
