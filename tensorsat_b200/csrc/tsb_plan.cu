@@ -117,7 +117,9 @@ struct tsb_plan {
   std::vector<SmallOp> small_ops;      // host copy
   SmallOp* d_small_ops = nullptr;
   void** d_ptrs = nullptr;             // device pointer table: [arena, out, leaf 0, leaf 1, ...]
-  void** h_ptrs = nullptr;             // pinned staging of the table
+  std::vector<void*> h_ptrs;           // host copy of the table (pageable: the async copy stages it)
+  bool mask_root = false;              // root keeps the sliced wires; a final masked sum selects the executed slices
+  int64_t mask_offset = -1;            // arena offset of the slice mask (u8, one entry per slice combination)
 };
 
 namespace {
@@ -327,7 +329,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   for (auto w : P.out_wires) if (S.count(w)) P.stack_out = true;
   // Tail of the tree: once the per-slice tensors are small again (with the sliced wires kept), the slices
   // are gathered into one tensor and the remaining steps run ONCE after the slice loop.
-  if (sliced_any && n_steps > 0 && !P.stack_out) {
+  if (sliced_any && n_steps > 0 && !P.stack_out && prod_ext(P.sliced, P.wext) <= 4096) {
     std::vector<int> parent(2 * L - 1, -1);
     for (int s = 0; s < n_steps; s++) { parent[path[s].first] = L + s; parent[path[s].second] = L + s; }
     auto lg_b = [&](int i) { return std::log2((double)P.nodes[i].reg_numel) + std::log2((double)P.nodes[i].s_numel); };
@@ -355,11 +357,10 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       if (nd.post) { nd.shared = true; continue; }
       if (!nd.shared && i != P.root && P.nodes[parent[i]].post) nd.gathered = true;
     }
-    if (P.nodes[P.root].post) {
-      // the sliced wires are ordinary summed wires of the last step: the result carries none of them
-      P.nodes[P.root].slab.clear();
-      P.nodes[P.root].s_numel = 1;
-    }
+    // A post root keeps the sliced wires as leading axes; one final masked sum over them selects the slices
+    // this call was asked to execute (other ranks execute the others), so that contributions that never
+    // pass through the slice loop are not counted once per rank.
+    P.mask_root = P.nodes[P.root].post;
   }
   if (P.mode == TSB_COUNT) {
     P.nodes[P.root].dtype = TSB_I64;
@@ -418,7 +419,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     op.alg_ops = 2.0 * std::exp2(lb + lm + ln + lk);
     P.ops.push_back(op);
   }
-  if (n_steps > 0 && !P.stack_out) P.nodes[P.root].is_out = true;
+  if (n_steps > 0 && !P.stack_out && !P.mask_root) P.nodes[P.root].is_out = true;
 
   // ---- kernel selection ------------------------------------------------------------------------
   const bool force_generic = (P.flags & TSB_PLAN_FORCE_GENERIC) != 0;
@@ -524,6 +525,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
       if (opnd >= 0 && P.nodes[opnd].shared) last_use[opnd] = std::max(last_use[opnd], n_pre + n_loop - 1);
   FreeList fl;
+  if (P.mask_root) P.mask_offset = fl.alloc((int64_t)P.nodes[P.root].s_numel);
   if (P.stack_out || (sliced_any && L == 1)) {
     // result buffer with the sliced output wires leading; combined across slices, permuted at the end
     PNode r;
@@ -627,7 +629,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     TSB_CUDA(cudaMemcpy(P.d_small_ops, P.small_ops.data(), P.small_ops.size() * sizeof(SmallOp), cudaMemcpyHostToDevice));
   }
   TSB_CUDA(cudaMalloc((void**)&P.d_ptrs, (size_t)(L + 2) * sizeof(void*)));
-  TSB_CUDA(cudaMallocHost((void**)&P.h_ptrs, (size_t)(L + 2) * sizeof(void*)));
+  P.h_ptrs.assign((size_t)L + 2, nullptr);
 
   // ---- info ------------------------------------------------------------------------------------
   P.info.n_slices = prod_ext(P.sliced, P.wext);
@@ -845,7 +847,7 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       P.h_ptrs[0] = base;
       P.h_ptrs[1] = out;
       for (int i = 0; i < P.n_leaves; i++) P.h_ptrs[2 + i] = const_cast<void*>(leaf_ptrs[i]);
-      TSB_CUDA(cudaMemcpyAsync(P.d_ptrs, P.h_ptrs, (size_t)(P.n_leaves + 2) * sizeof(void*), cudaMemcpyHostToDevice,
+      TSB_CUDA(cudaMemcpyAsync(P.d_ptrs, P.h_ptrs.data(), (size_t)(P.n_leaves + 2) * sizeof(void*), cudaMemcpyHostToDevice,
                                stream));
     }
     for (int g : P.gathered_nodes) TSB_CUDA(cudaMemsetAsync(base + P.nodes[g].offset, 0, P.nodes[g].bytes, stream));
@@ -915,6 +917,21 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       }
     }
     run_schedule(P.post_schedule);
+    if (P.mask_root) {
+      // out[o] = sum over sliced-wire combinations s in [slice_begin, slice_end) of root[s, o]
+      const PNode& r = P.nodes[P.root];
+      std::vector<uint8_t> mask((size_t)r.s_numel, 0);
+      for (int64_t sid = slice_begin; sid < slice_end; sid++) {
+        const std::vector<int64_t> digits = slice_digits(P, sid);
+        mask[(size_t)(shared_offset(P, r, digits) / r.reg_numel)] = 1;
+      }
+      uint8_t* d_mask = base + P.mask_offset;
+      TSB_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, stream));
+      const std::vector<int32_t> rw = r.stored();
+      contract2_impl(ctx, base + r.offset, (int)rw.size(), rw.data(), r.dtype, d_mask, (int)r.slab.size(), r.slab.data(),
+                     TSB_U8, out, (int)r.reg.size(), r.reg.data(), P.info.out_dtype, P.n_wires, P.wext.data(), P.mode, false,
+                     false, stream);
+    }
     if (P.stack_out) {
       // [sliced output wires][other output wires] -> requested output order
       const PNode& r = P.nodes[P.rnode];
@@ -939,7 +956,6 @@ int tsb_plan_destroy(tsb_plan* plan) {
     for (auto e : plan->ev) cudaEventDestroy(e);
     if (plan->d_small_ops) cudaFree(plan->d_small_ops);
     if (plan->d_ptrs) cudaFree(plan->d_ptrs);
-    if (plan->h_ptrs) cudaFreeHost(plan->h_ptrs);
     delete plan;
   }
   return TSB_OK;

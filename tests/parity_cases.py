@@ -335,6 +335,13 @@ def test_sliced_matches_unsliced_and_oracle(n, m, seed, target):
             assert int(full) == int(brute.sum())
         else:
             assert bool(full) == bool(brute.any())
+        # slice ranges (what the ranks of a multi-GPU job execute) combine to the whole
+        for bl in (-1, 4):
+            tc = TreeContraction(box_class, flat.wiring, tree=sliced, wire_is_free=free, batch_log2=bl)
+            k = sliced.num_slices // 3
+            parts = [tc.contract(flat, slice_range=r).tensor for r in ((0, k), (k, k), (k, sliced.num_slices))]
+            comb = parts[0] + parts[1] + parts[2] if mode == "count" else parts[0] | parts[1] | parts[2]
+            assert np.array_equal(comb, want)
 
 
 def test_sliced_output_wires_are_stacked():
