@@ -124,3 +124,98 @@ k_permute(const __grid_constant__ PermDesc d, const uint8_t* __restrict__ src, u
 }
 
 }  // namespace tsb
+
+namespace tsb {
+
+// ---- byte permutations with no low bit in place: 4x4 byte transposes in registers ---------------
+// When the two lowest source bits (a0, a1: the byte inside a source word) are not among the four lowest
+// destination bits (c0..c3: the byte inside a destination vector), a thread owns the 64 bytes spanned by
+// {a0, a1, c0, c1, c2, c3}: 16 source words (one per c-combination, each holding the 4 a-bytes) are read
+// with LDS.32, four 4x4 byte transposes (8 PRMT each) turn them into 16 destination words, and the four
+// a-combinations leave as four 16-byte stores.  4 LDS.32 + 8 PRMT per 16 output bytes instead of 16 LDS.U8.
+struct PermT4Desc {
+  PermDesc p;
+  BitRuns u2jd;        // work-item index (tile bits without a0, a1, c0..c3, in destination order) -> tile-dst index
+  int32_t a_dst[2];    // destination tile bit of a0, a1
+};
+
+TSB_D void transpose4x4_bytes(uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  // in: w_j byte i = M[j][i]; out: w_i byte j = M[j][i]
+  const uint32_t t0 = __byte_perm(w0, w1, 0x5140u);  // M00 M10 M01 M11
+  const uint32_t t1 = __byte_perm(w2, w3, 0x5140u);  // M20 M30 M21 M31
+  const uint32_t t2 = __byte_perm(w0, w1, 0x7362u);  // M02 M12 M03 M13
+  const uint32_t t3 = __byte_perm(w2, w3, 0x7362u);  // M22 M32 M23 M33
+  w0 = __byte_perm(t0, t1, 0x5410u);                 // M00 M10 M20 M30
+  w1 = __byte_perm(t0, t1, 0x7632u);                 // M01 M11 M21 M31
+  w2 = __byte_perm(t2, t3, 0x5410u);
+  w3 = __byte_perm(t2, t3, 0x7632u);
+}
+
+static __global__ void __launch_bounds__(kPermThreads)
+k_permute_t4(const __grid_constant__ PermT4Desc dd, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
+  TSB_DYN_SMEM(smem);
+  const PermDesc& d = dd.p;
+  constexpr int lo = 2;
+  const int nvec = 1 << (d.tbits - 4);
+  const int nwork = 1 << (d.tbits - 6);
+  uint64_t* t_src = (uint64_t*)(smem + (1u << d.tbits));
+  uint64_t* t_dst = t_src + (1u << (d.tbits - d.a_bits));
+  uint16_t* t_sb = (uint16_t*)(t_dst + (1u << (d.tbits - d.b_bits)));  // swizzled tile-src address of a work item
+  uint16_t* t_jd = t_sb + nwork;                                       // tile-dst index of a work item
+  for (int i = threadIdx.x; i < (1 << (d.tbits - d.a_bits)); i += blockDim.x) t_src[i] = deposit(d.src_hi, (uint64_t)i);
+  for (int i = threadIdx.x; i < (1 << (d.tbits - d.b_bits)); i += blockDim.x) t_dst[i] = deposit(d.dst_hi, (uint64_t)i);
+  for (int i = threadIdx.x; i < nwork; i += blockDim.x) {
+    const uint32_t jd = (uint32_t)deposit(dd.u2jd, (uint64_t)i);
+    t_jd[i] = (uint16_t)jd;
+    t_sb[i] = (uint16_t)perm_swz((uint32_t)deposit(d.d2s, (uint64_t)jd), lo);
+  }
+  uint32_t off[16];  // swizzled tile-src offsets of the 16 c-combinations
+#pragma unroll
+  for (int e = 0; e < 16; e++) off[e] = perm_swz((uint32_t)deposit(d.d2s, (uint64_t)e), lo);
+  __shared__ RunsSmem runs_s, runs_d;
+  runs_to_smem(d.cta_src, runs_s);
+  runs_to_smem(d.cta_dst, runs_d);
+  __syncthreads();
+  const uint32_t amask = (1u << d.a_bits) - 1u, bmask = (1u << d.b_bits) - 1u;
+  const uint32_t ja0 = 1u << dd.a_dst[0], ja1 = 1u << dd.a_dst[1];
+  int64_t tile = blockIdx.x;
+  uint64_t off_s = tile < d.n_tiles ? deposit_warp(runs_s, (uint64_t)tile) : 0;
+  uint64_t off_d = tile < d.n_tiles ? deposit_warp(runs_d, (uint64_t)tile) : 0;
+  for (; tile < d.n_tiles; tile += gridDim.x) {
+    const uint8_t* s0 = src + off_s;
+    uint8_t* d0 = dst + off_d;
+    if (tile + gridDim.x < d.n_tiles) {
+      off_s = deposit_warp(runs_s, (uint64_t)(tile + gridDim.x));
+      off_d = deposit_warp(runs_d, (uint64_t)(tile + gridDim.x));
+    }
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint32_t js = (uint32_t)v << 4;
+      uint4 w = *(const uint4*)(s0 + ((js & amask) | t_src[js >> d.a_bits]));
+      const uint32_t sa = perm_swz(js, lo);
+      const uint32_t x = ((sa ^ js) >> 2) & 3u;
+      if (x & 1u) { uint32_t t = w.x; w.x = w.y; w.y = t; t = w.z; w.z = w.w; w.w = t; }
+      if (x & 2u) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
+      *(uint4*)(smem + (sa & ~15u)) = w;
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < nwork; u += blockDim.x) {
+      const uint32_t sb = t_sb[u] & ~3u;  // word address (the a-bits are the byte lanes)
+      uint32_t W[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) W[e] = *(const uint32_t*)(smem + (sb ^ off[e]));
+      // W[c3c2c1c0] byte a  ->  per (c3,c2): transpose over (c1,c0) x a
+#pragma unroll
+      for (int q = 0; q < 4; q++) transpose4x4_bytes(W[4 * q], W[4 * q + 1], W[4 * q + 2], W[4 * q + 3]);
+      // now W[4*q + a] holds bytes c1c0 = 0..3 for (c3,c2) = q and a-combination a
+      const uint32_t jd = t_jd[u];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const uint32_t j = jd | ((a & 1) ? ja0 : 0u) | ((a & 2) ? ja1 : 0u);
+        *(uint4*)(d0 + ((j & bmask) | t_dst[j >> d.b_bits])) = make_uint4(W[a], W[4 + a], W[8 + a], W[12 + a]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tsb

@@ -233,7 +233,8 @@ inline bool has_dups(const BitLabels& b) {
 // ---- permutation lowering ---------------------------------------------------------------
 // src_bits / dst_bits: the same label set in two orders (MSB first); esz_log2 extra identical low bits.
 // Returns false if the fast kernel cannot serve it (caller falls back to the generic kernel).
-inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits, int esz_log2, PermDesc& d, int& G) {
+inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits, int esz_log2, PermDesc& d, int& G,
+                           PermT4Desc* t4 = nullptr, bool* use_t4 = nullptr) {
   const int r = (int)src_bits.size() + esz_log2;  // in byte-address bits
   if (r < 9 || r > 62) return false;
   // label at each byte-address bit of src/dst (element-size bits get pseudo labels -1-q)
@@ -281,7 +282,39 @@ inline bool make_perm_desc(const BitLabels& src_bits, const BitLabels& dst_bits,
   if (cs.n > 32 || cd.n > 32) return false;  // one run per lane in the kernel
   d.cta_src = cs; d.cta_dst = cd;
   d.n_tiles = int64_t(1) << (r - tbits);
+  if (t4 && use_t4) {
+    *use_t4 = false;
+    // 4x4 register transposes: the two lowest source bits are not among the four lowest destination bits
+    if (g == 0 && tbits >= 8) {
+      const int a0 = tdpos[ts[0]], a1 = tdpos[ts[1]];
+      if (a0 >= 4 && a1 >= 4) {
+        *t4 = PermT4Desc{};
+        t4->p = d;
+        t4->a_dst[0] = a0; t4->a_dst[1] = a1;
+        int ui = 0;
+        for (int i = 4; i < tbits; i++) {
+          if (i == a0 || i == a1) continue;
+          runs_add(t4->u2jd, ui, i);
+          ui++;
+        }
+        *use_t4 = true;
+      }
+    }
+  }
   return true;
+}
+
+inline size_t perm_t4_smem_bytes(const PermDesc& d) {
+  return (size_t(1) << d.tbits) + 8 * (size_t(1) << (d.tbits - d.a_bits)) + 8 * (size_t(1) << (d.tbits - d.b_bits)) +
+         4 * (size_t(1) << (d.tbits - 6)) + 16;
+}
+
+inline void launch_permute_t4(tsb_ctx* ctx, const PermT4Desc& d, const void* src, void* dst, cudaStream_t stream) {
+  const size_t smem = perm_t4_smem_bytes(d.p);
+  const int grid = (int)std::min<int64_t>(d.p.n_tiles, (int64_t)ctx->sm_count * 8);
+  TSB_LAUNCH(k_permute_t4, dim3(grid), dim3(kPermThreads), smem, stream, d, (const uint8_t*)src, (uint8_t*)dst);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
 }
 
 inline size_t perm_smem_bytes(const PermDesc& d) {
@@ -318,9 +351,12 @@ inline void permute_bits(tsb_ctx* ctx, const void* src, const BitLabels& src_bit
   }
   const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
   PermDesc pd;
+  PermT4Desc t4;
+  bool use_t4 = false;
   int G = 1;
-  if (aligned && !has_dups(src_bits) && make_perm_desc(src_bits, dst_bits, ilog2(elem_size), pd, G)) {
-    launch_permute_fast(ctx, pd, G, src, dst, stream);
+  if (aligned && !has_dups(src_bits) && make_perm_desc(src_bits, dst_bits, ilog2(elem_size), pd, G, &t4, &use_t4)) {
+    if (use_t4) launch_permute_t4(ctx, t4, src, dst, stream);
+    else launch_permute_fast(ctx, pd, G, src, dst, stream);
     return;
   }
   auto sp = positions(src_bits);

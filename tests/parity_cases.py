@@ -218,6 +218,18 @@ def test_permute_random(seed):
     assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm))
 
 
+def test_permute_byte_transposes_in_registers():
+    """Permutations that move the lowest axes away (4x4 byte-transpose kernel) incl. full reversal."""
+    rng = np.random.default_rng(6)
+    for r in (9, 12, 14, min(17, SCALE["big_bits"])):
+        t = rng.integers(0, 2, size=(2,) * r, dtype=np.uint8)
+        perms = [list(range(r))[::-1], list(range(2, r)) + [0, 1], [r - 1, r - 2] + list(range(r - 2))]
+        perms.append([int(p) for p in rng.permutation(r - 6)] + [r - 1, r - 2, r - 6, r - 5, r - 4, r - 3])
+        for perm in perms:
+            box = CudaFinRel(t).rewire(perm)
+            assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm)), (r, perm)
+
+
 def test_permute_keeps_low_axes_and_wide_elements():
     rng = np.random.default_rng(5)
     r = 13
