@@ -20,6 +20,7 @@ namespace tsb {
 
 constexpr int kPermMaxTileBits = 14;  // 16 KiB tile
 constexpr int kPermThreads = 256;
+constexpr int kPermMaxVecPerThread = (1 << (kPermMaxTileBits - 4)) / kPermThreads;  // 4
 
 struct PermDesc {
   int32_t g;          // log2 of the gather group in bytes (0..4)
@@ -67,25 +68,52 @@ k_permute(const __grid_constant__ PermDesc d, const uint8_t* __restrict__ src, u
   int64_t tile = blockIdx.x;
   uint64_t off_s = tile < d.n_tiles ? deposit_warp(runs_s, (uint64_t)tile) : 0;
   uint64_t off_d = tile < d.n_tiles ? deposit_warp(runs_d, (uint64_t)tile) : 0;
+  // software pipeline: the global loads of tile i+1 are issued (into registers) before the gather / store
+  // phase of tile i, so that their latency overlaps with it
+  uint4 pre[kPermMaxVecPerThread];
+  if (tile < d.n_tiles) {
+#pragma unroll
+    for (int q = 0; q < kPermMaxVecPerThread; q++) {
+      const int v = threadIdx.x + q * kPermThreads;
+      if (v < nvec) {
+        const uint32_t js = (uint32_t)v << 4;
+        pre[q] = *(const uint4*)(src + off_s + ((js & amask) | t_src[js >> d.a_bits]));
+      }
+    }
+  }
   for (; tile < d.n_tiles; tile += gridDim.x) {
-    const uint8_t* s0 = src + off_s;
     uint8_t* d0 = dst + off_d;
-    if (tile + gridDim.x < d.n_tiles) {  // next tile's offsets, one bit run per lane (uniform branch)
+    const bool more = tile + gridDim.x < d.n_tiles;
+    if (more) {  // next tile's offsets, one bit run per lane (uniform branch)
       off_s = deposit_warp(runs_s, (uint64_t)(tile + gridDim.x));
       off_d = deposit_warp(runs_d, (uint64_t)(tile + gridDim.x));
     }
-    // ---- load phase: tile-src order, 16-byte vectors, swizzled into shared memory
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-      const uint32_t js = (uint32_t)v << 4;
-      uint4 w = *(const uint4*)(s0 + ((js & amask) | t_src[js >> d.a_bits]));
-      const uint32_t sa = perm_swz(js, lo);
-      // the swizzle may flip address bits 2,3 (word within the vector): permute registers instead
-      const uint32_t x = ((sa ^ js) >> 2) & 3u;
-      if (x & 1u) { uint32_t t = w.x; w.x = w.y; w.y = t; t = w.z; w.z = w.w; w.w = t; }
-      if (x & 2u) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
-      *(uint4*)(smem + (sa & ~15u)) = w;
+    // ---- registers -> shared memory (tile-src order, swizzled)
+#pragma unroll
+    for (int q = 0; q < kPermMaxVecPerThread; q++) {
+      const int v = threadIdx.x + q * kPermThreads;
+      if (v < nvec) {
+        const uint32_t js = (uint32_t)v << 4;
+        uint4 w = pre[q];
+        const uint32_t sa = perm_swz(js, lo);
+        // the swizzle may flip address bits 2,3 (word within the vector): permute registers instead
+        const uint32_t x = ((sa ^ js) >> 2) & 3u;
+        if (x & 1u) { uint32_t t = w.x; w.x = w.y; w.y = t; t = w.z; w.z = w.w; w.w = t; }
+        if (x & 2u) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
+        *(uint4*)(smem + (sa & ~15u)) = w;
+      }
     }
     __syncthreads();
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < kPermMaxVecPerThread; q++) {
+        const int v = threadIdx.x + q * kPermThreads;
+        if (v < nvec) {
+          const uint32_t js = (uint32_t)v << 4;
+          pre[q] = *(const uint4*)(src + off_s + ((js & amask) | t_src[js >> d.a_bits]));
+        }
+      }
+    }
     // ---- store phase: tile-dst order, gather groups of G bytes, 16-byte vectors out
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
       const uint32_t jd = (uint32_t)v << 4;
@@ -181,23 +209,48 @@ k_permute_t4(const __grid_constant__ PermT4Desc dd, const uint8_t* __restrict__ 
   int64_t tile = blockIdx.x;
   uint64_t off_s = tile < d.n_tiles ? deposit_warp(runs_s, (uint64_t)tile) : 0;
   uint64_t off_d = tile < d.n_tiles ? deposit_warp(runs_d, (uint64_t)tile) : 0;
+  uint4 pre[kPermMaxVecPerThread];
+  if (tile < d.n_tiles) {
+#pragma unroll
+    for (int q = 0; q < kPermMaxVecPerThread; q++) {
+      const int v = threadIdx.x + q * kPermThreads;
+      if (v < nvec) {
+        const uint32_t js = (uint32_t)v << 4;
+        pre[q] = *(const uint4*)(src + off_s + ((js & amask) | t_src[js >> d.a_bits]));
+      }
+    }
+  }
   for (; tile < d.n_tiles; tile += gridDim.x) {
-    const uint8_t* s0 = src + off_s;
     uint8_t* d0 = dst + off_d;
-    if (tile + gridDim.x < d.n_tiles) {
+    const bool more = tile + gridDim.x < d.n_tiles;
+    if (more) {
       off_s = deposit_warp(runs_s, (uint64_t)(tile + gridDim.x));
       off_d = deposit_warp(runs_d, (uint64_t)(tile + gridDim.x));
     }
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-      const uint32_t js = (uint32_t)v << 4;
-      uint4 w = *(const uint4*)(s0 + ((js & amask) | t_src[js >> d.a_bits]));
-      const uint32_t sa = perm_swz(js, lo);
-      const uint32_t x = ((sa ^ js) >> 2) & 3u;
-      if (x & 1u) { uint32_t t = w.x; w.x = w.y; w.y = t; t = w.z; w.z = w.w; w.w = t; }
-      if (x & 2u) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
-      *(uint4*)(smem + (sa & ~15u)) = w;
+#pragma unroll
+    for (int q = 0; q < kPermMaxVecPerThread; q++) {
+      const int v = threadIdx.x + q * kPermThreads;
+      if (v < nvec) {
+        const uint32_t js = (uint32_t)v << 4;
+        uint4 w = pre[q];
+        const uint32_t sa = perm_swz(js, lo);
+        const uint32_t x = ((sa ^ js) >> 2) & 3u;
+        if (x & 1u) { uint32_t t = w.x; w.x = w.y; w.y = t; t = w.z; w.z = w.w; w.w = t; }
+        if (x & 2u) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
+        *(uint4*)(smem + (sa & ~15u)) = w;
+      }
     }
     __syncthreads();
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < kPermMaxVecPerThread; q++) {
+        const int v = threadIdx.x + q * kPermThreads;
+        if (v < nvec) {
+          const uint32_t js = (uint32_t)v << 4;
+          pre[q] = *(const uint4*)(src + off_s + ((js & amask) | t_src[js >> d.a_bits]));
+        }
+      }
+    }
     for (int u = threadIdx.x; u < nwork; u += blockDim.x) {
       const uint32_t sb = t_sb[u] & ~3u;  // word address (the a-bits are the byte lanes)
       uint32_t W[16];

@@ -4,6 +4,7 @@
 // operand, which kernel can serve a step, and how its descriptor is filled.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <set>
@@ -355,7 +356,8 @@ inline void permute_bits(tsb_ctx* ctx, const void* src, const BitLabels& src_bit
   bool use_t4 = false;
   int G = 1;
   if (aligned && !has_dups(src_bits) && make_perm_desc(src_bits, dst_bits, ilog2(elem_size), pd, G, &t4, &use_t4)) {
-    if (use_t4) launch_permute_t4(ctx, t4, src, dst, stream);
+    static const int t4_mode = [] { const char* e = getenv("TSB_PERMUTE_T4"); return e ? atoi(e) : 1; }();  // tuning knob
+    if (use_t4 && t4_mode) launch_permute_t4(ctx, t4, src, dst, stream);
     else launch_permute_fast(ctx, pd, G, src, dst, stream);
     return;
   }
