@@ -1,105 +1,136 @@
 """
-Binary-circuit gates and arithmetic circuits, stated as in the reference
-(tensorsat/lib/bincirc.py:28-177).  They only define the *inputs* of the contraction
-hot path (leaf tensors + wiring); the leaves are 2-, 4- or 8-byte 0/1 tensors that are
-uploaded once per contraction.
+Gate relations and arithmetic circuits that define the benchmark networks of the contraction hot
+path (the host-side counterpart of the reference's ``tensorsat/lib/bincirc.py:28-177``).
+
+Only the *inputs* of the executor are produced here: 2-, 4- and 8-byte 0/1 leaf tensors and the
+wiring between them.  Block and wire creation order follows the reference exactly, because the
+flat wiring (wire numbers, slot order) is part of the benchmark definition; the wiring digests of
+``tests/golden/instances.json`` pin it.
 """
 
 from __future__ import annotations
 
-from itertools import product
-from typing import Final
+from typing import Callable, Final
 
 from ..diagrams import Diagram, DiagramBuilder, FinSet, Wire
 from ..lang.fin_rel import FinRel
 
 bit: Final[FinSet] = FinSet(2)
-"""The set {0, 1} of binary values (bincirc.py:28)."""
+"""The two-element set of binary values."""
 
 
 def bits(n: int) -> tuple[FinSet, ...]:
-    """Shape consisting of the given number of bits (bincirc.py:32-36)."""
+    """Shape made of ``n`` bits."""
     if n < 0:
         raise ValueError("Number of bits must be non-negative.")
-    return (bit,) * n
+    return tuple(bit for _ in range(n))
 
 
 bits2: Final = bits(2)
 
-# Gate relations as function graphs, input ports first (bincirc.py:42-73).
-not_: Final[FinRel] = FinRel.from_callable(bit, bit, lambda b: 1 - b, name="not_")
-and_: Final[FinRel] = FinRel.from_callable(bits2, bit, lambda a, b: a & b, name="and_")
-or_: Final[FinRel] = FinRel.from_callable(bits2, bit, lambda a, b: a | b, name="or_")
-impl_: Final[FinRel] = FinRel.from_callable(bits2, bit, lambda a, b: (1 - a) | b, name="impl_")
-biimpl_: Final[FinRel] = FinRel.from_callable(
-    bits2, bit, lambda a, b: (a & b) | ((1 - a) & (1 - b)), name="biimpl_"
-)
-xor_: Final[FinRel] = FinRel.from_callable(bits2, bit, lambda a, b: a ^ b, name="xor_")
+
+def _gate(name: str, arity: int, fn: Callable[..., int]) -> FinRel:
+    """Graph of a boolean function: input ports first, the output port last."""
+    return FinRel.from_callable(bits(arity), bit, fn, name=name)
+
+
+_TRUTH: Final[dict[str, tuple[int, Callable[..., int]]]] = {
+    "not_": (1, lambda a: a ^ 1),
+    "and_": (2, lambda a, b: a & b),
+    "or_": (2, lambda a, b: a | b),
+    "impl_": (2, lambda a, b: (a ^ 1) | b),
+    "biimpl_": (2, lambda a, b: (a ^ b) ^ 1),
+    "xor_": (2, lambda a, b: a ^ b),
+}
+
+not_: Final[FinRel] = _gate("not_", *_TRUTH["not_"])
+and_: Final[FinRel] = _gate("and_", *_TRUTH["and_"])
+or_: Final[FinRel] = _gate("or_", *_TRUTH["or_"])
+impl_: Final[FinRel] = _gate("impl_", *_TRUTH["impl_"])
+biimpl_: Final[FinRel] = _gate("biimpl_", *_TRUTH["biimpl_"])
+xor_: Final[FinRel] = _gate("xor_", *_TRUTH["xor_"])
+
 bit_0: Final[FinRel] = FinRel.singleton(bit, 0, name="bit_0")
 bit_1: Final[FinRel] = FinRel.singleton(bit, 1, name="bit_1")
-bit_unk: Final[FinRel] = FinRel.from_set(bit, {0, 1}, name="bit_unk")
+bit_unk: Final[FinRel] = FinRel.from_set(bit, (0, 1), name="bit_unk")
+"""Constant 0, constant 1 and the unconstrained bit {0, 1}."""
 
 
-@Diagram.from_recipe
-def half_adder(diag: DiagramBuilder) -> None:
-    """Half adder (bincirc.py:91-103)."""
-    a, b = diag.add_inputs(bits(2))
-    (s,) = xor_ @ diag[a, b]
-    (c,) = and_ @ diag[a, b]
-    diag.add_outputs([s, c])
+def _half_adder(circ: DiagramBuilder) -> None:
+    x, y = circ.add_inputs(bits2)
+    total = (xor_ @ circ[x, y])[0]
+    carry = (and_ @ circ[x, y])[0]
+    circ.add_outputs((total, carry))
 
 
-@Diagram.from_recipe
-def full_adder(diag: DiagramBuilder) -> None:
-    """Full adder (bincirc.py:106-121)."""
-    a, b, c_in = diag.add_inputs(bits(3))
-    (x1,) = xor_ @ diag[a, b]
-    (x2,) = and_ @ diag[a, b]
-    (x3,) = and_ @ diag[x1, c_in]
-    (s,) = xor_ @ diag[x1, c_in]
-    (c_out,) = or_ @ diag[x2, x3]
-    diag.add_outputs([s, c_out])
+def _full_adder(circ: DiagramBuilder) -> None:
+    x, y, carry_in = circ.add_inputs(bits(3))
+    partial = (xor_ @ circ[x, y])[0]
+    gen = (and_ @ circ[x, y])[0]
+    prop = (and_ @ circ[partial, carry_in])[0]
+    total = (xor_ @ circ[partial, carry_in])[0]
+    carry_out = (or_ @ circ[gen, prop])[0]
+    circ.add_outputs((total, carry_out))
 
 
-@Diagram.recipe
-def rc_adder(diag: DiagramBuilder, num_bits: int) -> None:
-    """Ripple-carry adder (bincirc.py:124-142)."""
-    if num_bits <= 0:
-        raise ValueError("Number of bits must be positive.")
-    a = diag.add_inputs(bits(num_bits))
-    b = diag.add_inputs(bits(num_bits))
-    c = diag.add_input(bit)
-    for i in range(num_bits):
-        s, c = full_adder @ diag[a[i], b[i], c]
-        diag.add_output(s)
-    diag.add_output(c)
+half_adder: Final[Diagram] = Diagram.from_recipe(_half_adder)
+"""(a, b) -> (sum, carry)."""
+
+full_adder: Final[Diagram] = Diagram.from_recipe(_full_adder)
+"""(a, b, carry_in) -> (sum, carry_out)."""
 
 
 @Diagram.recipe
-def wallace_multiplier(diag: DiagramBuilder, num_bits: int) -> None:
-    """Wallace-tree multiplier (bincirc.py:145-177)."""
+def rc_adder(circ: DiagramBuilder, num_bits: int) -> None:
+    """Ripple-carry adder of two ``num_bits``-bit numbers with carry in / carry out."""
     if num_bits <= 0:
         raise ValueError("Number of bits must be positive.")
-    a = diag.add_inputs(bits(num_bits))
-    b = diag.add_inputs(bits(num_bits))
-    layer: dict[int, list[Wire]] = {}
-    for i, j in product(range(num_bits), repeat=2):
-        (_out,) = and_ @ diag[a[i], b[j]]
-        layer.setdefault(i + j, []).append(_out)
-    while any(len(wires) > 1 for wires in layer.values()):
-        new_layer: dict[int, list[Wire]] = {}
-        for weight, wires in layer.items():
-            num_fulladd, _r = divmod(len(wires), 3)
-            for idx in range(num_fulladd):
-                s, c_out = full_adder @ diag[wires[3 * idx : 3 * idx + 3]]
-                new_layer.setdefault(weight, []).append(s)
-                new_layer.setdefault(weight + 1, []).append(c_out)
-            if _r == 2:
-                s, c_out = half_adder @ diag[wires[-2:]]
-                new_layer.setdefault(weight, []).append(s)
-                new_layer.setdefault(weight + 1, []).append(c_out)
-            elif _r == 1:
-                new_layer.setdefault(weight, []).append(wires[-1])
-        layer = new_layer
-    assert all(len(wires) == 1 for wires in layer.values())
-    diag.add_outputs(wires[0] for wires in layer.values())
+    xs = circ.add_inputs(bits(num_bits))
+    ys = circ.add_inputs(bits(num_bits))
+    carry = circ.add_input(bit)
+    for x, y in zip(xs, ys):
+        total, carry = full_adder @ circ[x, y, carry]
+        circ.add_output(total)
+    circ.add_output(carry)
+
+
+def _compress_column(circ: DiagramBuilder, column: list[Wire]) -> tuple[list[Wire], list[Wire]]:
+    """One Wallace step on the wires of one weight: full adders on triples, a half adder on a remaining
+    pair, a remaining single wire passes through.  Returns (wires kept at this weight, carries)."""
+    kept: list[Wire] = []
+    carries: list[Wire] = []
+    triples, rest = divmod(len(column), 3)
+    for t in range(triples):
+        s, c = full_adder @ circ[column[3 * t : 3 * t + 3]]
+        kept.append(s)
+        carries.append(c)
+    if rest == 2:
+        s, c = half_adder @ circ[column[-2:]]
+        kept.append(s)
+        carries.append(c)
+    elif rest == 1:
+        kept.append(column[-1])
+    return kept, carries
+
+
+@Diagram.recipe
+def wallace_multiplier(circ: DiagramBuilder, num_bits: int) -> None:
+    """Wallace-tree multiplier: ``num_bits`` + ``num_bits`` input ports, then the product bits by weight."""
+    if num_bits <= 0:
+        raise ValueError("Number of bits must be positive.")
+    xs = circ.add_inputs(bits(num_bits))
+    ys = circ.add_inputs(bits(num_bits))
+    columns: list[list[Wire]] = [[] for _ in range(2 * num_bits - 1)]
+    for i, x in enumerate(xs):
+        for j, y in enumerate(ys):
+            columns[i + j].append((and_ @ circ[x, y])[0])
+    while max(len(col) for col in columns) > 1:
+        nxt: list[list[Wire]] = [[] for _ in range(len(columns) + 1)]
+        for weight, column in enumerate(columns):
+            kept, carries = _compress_column(circ, column)
+            nxt[weight].extend(kept)
+            nxt[weight + 1].extend(carries)
+        while nxt and not nxt[-1]:
+            nxt.pop()
+        columns = nxt
+    circ.add_outputs(col[0] for col in columns)

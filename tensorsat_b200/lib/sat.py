@@ -1,171 +1,174 @@
 """
-CNF instances and their relation networks, stated as in the reference
-(tensorsat/lib/sat.py:43-262).  The generator must reproduce the reference's RNG stream
-exactly, because the benchmark instances are defined by ``(k, n, m, seed)``.
+CNF instances as relation networks: the benchmark inputs of the contraction hot path
+(host-side counterpart of the reference's ``tensorsat/lib/sat.py:43-262``).
+
+Two things here are part of the benchmark definition and are pinned by ``tests/golden``:
+the random generator must consume the numpy RNG stream exactly like the reference
+(``sat.py:63-78``), and the "bintree" network must number wires and order blocks exactly like
+``sat.py:248-262``.
 """
 
 from __future__ import annotations
 
 import re
-from collections.abc import Sequence
+from collections.abc import Iterator, Sequence
 from math import comb
 
 import numpy as np
 
 from ..diagrams import Diagram, DiagramBuilder, Wire, Wiring
-from .bincirc import bit, bit_0, bit_1, bit_unk, bits, not_, or_
+from . import bincirc as bc
 
 Clause = tuple[int, ...]
+_HEADER = re.compile(r"p cnf ([0-9]+) ([0-9]+)")
+_INPUT_BOXES = {"0": bc.bit_0, "1": bc.bit_1, "?": bc.bit_unk}
+
+
+def _draw_clauses(k: int, n: int, rng: np.random.Generator) -> Iterator[Clause]:
+    """Endless stream of random k-clauses; two RNG calls per clause, as in the reference."""
+    variables, polarities = range(n), range(2)
+    while True:
+        chosen = rng.choice(variables, size=k, replace=False)
+        negated = rng.choice(polarities, size=k)
+        yield tuple(sorted(-(int(v) + 1) if int(s) else int(v) + 1 for v, s in zip(chosen, negated)))
+
+
+def parse_dimacs(text: str) -> tuple[int, tuple[Clause, ...]]:
+    """DIMACS with the reference's conventions (``sat.py:80-100``): comment lines start with ``c``,
+    one clause per line, literals separated by single spaces, the trailing ``0`` is dropped."""
+    rows = [ln.strip() for ln in text.strip().split("\n")]
+    rows = [ln for ln in rows if ln and not ln.startswith("c")]
+    head = _HEADER.match(rows[0]) if rows else None
+    if head is None:
+        raise ValueError("DIMACS code must start with 'p cnf <num vars> <num clauses>'.")
+    num_vars, num_clauses = int(head.group(1)), int(head.group(2))
+    clauses = tuple(tuple(int(tok) for tok in ln.split(" "))[:-1] for ln in rows[1:])
+    if len(clauses) != num_clauses:
+        raise ValueError("Number of clauses does not match the specified number.")
+    return num_vars, clauses
+
+
+def _check_literals(num_vars: int, clauses: Sequence[Sequence[int]]) -> None:
+    if any(abs(lit) > num_vars for clause in clauses for lit in clause):
+        raise ValueError("Clauses contain invalid variables.")
 
 
 class CNFInstance:
-    """A SAT instance in CNF form (tensorsat/lib/sat.py:40-275)."""
-
-    __slots__ = ("_num_vars", "_clauses")
+    """A SAT instance in conjunctive normal form."""
 
     def __init__(self, num_vars: int, clauses: Sequence[Sequence[int]]) -> None:
-        clauses = tuple(tuple(int(x) for x in c) for c in clauses)
-        if num_vars < max(abs(lit) for clause in clauses for lit in clause):
-            raise ValueError("Clauses contain invalid variables.")
-        self._num_vars = int(num_vars)
-        self._clauses = clauses
+        frozen = tuple(tuple(int(lit) for lit in clause) for clause in clauses)
+        _check_literals(num_vars, frozen)
+        self._n = int(num_vars)
+        self._clauses = frozen
 
+    # ------------------------------------------------------------------ constructors
     @classmethod
-    def random(
-        cls, k: int, n: int, m: int, *, rng: int | np.random.Generator | None = None
-    ) -> "CNFInstance":
-        """Random k-SAT, n variables, m distinct clauses (sat.py:43-78; same RNG calls)."""
+    def random(cls, k: int, n: int, m: int, *, rng: int | np.random.Generator | None = None) -> "CNFInstance":
+        """``m`` distinct random ``k``-clauses over ``n`` variables (https://arxiv.org/abs/1405.3558)."""
         if k <= 0:
             raise ValueError("Clause size 'k' must be positive.")
         if n < k:
             raise ValueError(f"Number of variables 'n' must be at least {k = }.")
         if m <= 0:
             raise ValueError("Number of clauses 'm' must be positive.")
-        if m > comb(n, k) * 2**k:
-            raise ValueError(f"Number of clauses 'm' cannot exceed {comb(n, k)*2**k = }")
-        if not isinstance(rng, np.random.Generator):
-            rng = np.random.default_rng(rng)
-        clauses: list[Clause] = []
-        seen: set[Clause] = set()
-        while len(clauses) < m:
-            vs = [int(v) for v in rng.choice(range(n), size=k, replace=False)]
-            signs = [int(s) for s in rng.choice(range(2), size=k)]
-            clause = tuple(sorted(v + 1 if s == 0 else -v - 1 for v, s in zip(vs, signs)))
-            if clause not in seen:
-                clauses.append(clause)
-                seen.add(clause)
-        return cls(n, clauses)
+        limit = comb(n, k) * 2**k
+        if m > limit:
+            raise ValueError(f"Number of clauses 'm' cannot exceed {limit}")
+        gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+        picked: dict[Clause, None] = {}
+        for clause in _draw_clauses(k, n, gen):
+            picked.setdefault(clause)
+            if len(picked) == m:
+                break
+        return cls(n, tuple(picked))
 
     @classmethod
     def from_dimacs(cls, dimacs: str) -> "CNFInstance":
-        """DIMACS parser with the reference's conventions (sat.py:80-100): one clause per
-        line, single-space separated, trailing ``0`` dropped, lines starting with ``c``
-        skipped."""
         if not isinstance(dimacs, str):
             raise TypeError("DIMACS code must be a string.")
-        lines = [
-            stripped
-            for line in dimacs.strip().split("\n")
-            if (stripped := line.strip()) and not stripped.startswith("c")
-        ]
-        start = re.compile(r"p cnf ([0-9]+) ([0-9]+)").match(lines[0]) if lines else None
-        if not start:
-            raise ValueError("DIMACS code must start with 'p cnf <num vars> <num clauses>'.")
-        num_vars, num_clauses = map(int, start.groups())
-        clauses = tuple(tuple(map(int, line.split(" ")))[:-1] for line in lines[1:])
-        if len(clauses) != num_clauses:
-            raise ValueError("Number of clauses does not match the specified number.")
-        if num_vars < max(abs(lit) for clause in clauses for lit in clause):
-            raise ValueError("Clauses contain invalid variables.")
-        return cls(num_vars, clauses)
+        return cls(*parse_dimacs(dimacs))
 
+    # ------------------------------------------------------------------ data
     @property
     def num_vars(self) -> int:
-        return self._num_vars
+        return self._n
 
     @property
     def clauses(self) -> tuple[Clause, ...]:
         return self._clauses
 
     def to_dimacs(self) -> str:
-        lines = [
-            f"p cnf {self.num_vars} {len(self.clauses)}",
-            *(f"{' '.join(map(str, clause))} 0" for clause in self.clauses),
-        ]
-        return "\n".join(lines)
+        body = [" ".join(str(lit) for lit in clause) + " 0" for clause in self._clauses]
+        return "\n".join([f"p cnf {self._n} {len(self._clauses)}", *body])
 
-    def _normalize_inputs(self, inputs: str | int | None) -> str:
-        n = self.num_vars
+    # ------------------------------------------------------------------ networks
+    def _input_spec(self, inputs: str | int | None) -> str:
+        if inputs is None:
+            return "?" * self._n
         if isinstance(inputs, int):
             if inputs < 0:
                 raise ValueError("Inputs must be specified by a non-negative number.")
-            inputs = f"{inputs:0>{n}b}"
-        elif inputs is None:
-            inputs = "?" * n
-        else:
-            if not isinstance(inputs, str):
-                raise TypeError("Input specification must be a string, an int or None.")
-            if not all(b in "01?_" for b in inputs):
+            spec = format(inputs, "b").rjust(self._n, "0")
+        elif isinstance(inputs, str):
+            spec = inputs
+            if set(spec) - set("01?_"):
                 raise ValueError("Input specification characters must be '0', '1', '?' or '_'.")
-        if len(inputs) != n:
+        else:
+            raise TypeError("Input specification must be a string, an int or None.")
+        if len(spec) != self._n:
             raise ValueError(
-                f"Expected input specification string to be {n} characters long,"
-                f" found {len(inputs)} characters instead."
+                f"Expected input specification string to be {self._n} characters long,"
+                f" found {len(spec)} characters instead."
             )
-        return inputs
+        return spec
 
     def inputs(self, inputs: str | int | None, /, *, discard_unk: bool = False) -> Diagram:
-        """Diagram fixing each variable to 0 / 1 / unknown (sat.py:165-206).
+        """One box per variable — ``'0'`` / ``'1'`` fix it, ``'?'`` leaves it unknown (``sat.py:165-206``).
 
-        ``'_'`` (leave the input open) is accepted by the reference's validation but its
-        builder branch is dead code (``case None`` never matches a character, sat.py:202)
-        and trips the ``assert w == i`` that follows; here it raises ``ValueError``.
+        With ``discard_unk`` unknown variables get a bare wire instead of a ``bit_unk`` box.  ``'_'`` passes
+        the reference's validation but its builder branch is dead code there (``sat.py:202``); it is rejected.
         """
-        inputs = self._normalize_inputs(inputs)
         builder = DiagramBuilder()
-        for i, b in enumerate(inputs):
-            w: Wire
-            if b == "0":
-                (w,) = bit_0 @ builder
-            elif b == "1":
-                (w,) = bit_1 @ builder
-            elif b == "?":
-                if discard_unk:
-                    w = builder.add_wire(bit)
-                else:
-                    (w,) = bit_unk @ builder
-            else:
+        for var, ch in enumerate(self._input_spec(inputs)):
+            if ch == "_":
                 raise ValueError("Open inputs ('_') are not supported.")
-            assert w == i
+            if ch == "?" and discard_unk:
+                wire = builder.add_wire(bc.bit)
+            else:
+                (wire,) = _INPUT_BOXES[ch] @ builder
+            assert wire == var
         builder.add_outputs(builder.wires)
         return builder.diagram()
 
     def diagram(self, *, mode: str = "bintree") -> Diagram:
-        if mode == "bintree":
-            return self._build_diagram_bintree()
-        raise NotImplementedError(f"Unknown diagram mode for CNFInstance: {mode!r}")
-
-    def contraction_wiring(self, *, mode: str = "bintree") -> Wiring:
-        """Wiring shared by every ``inputs(...) >> diagram()`` (sat.py:231-246)."""
-        return (self.inputs(0) >> self.diagram(mode=mode)).flatten().wiring
-
-    def _build_diagram_bintree(self) -> Diagram:
-        """One balanced OR tree per clause, ``bit_1`` on its output (sat.py:248-262)."""
+        if mode != "bintree":
+            raise NotImplementedError(f"Unknown diagram mode for CNFInstance: {mode!r}")
         builder = DiagramBuilder()
-        builder.add_inputs(bits(self.num_vars))
-        for clause in self.clauses:
-            layer = [x - 1 if x > 0 else (not_ @ builder[-x - 1])[0] for x in clause]
-            while (n := len(layer)) > 1:
-                new_layer = [(or_ @ builder[layer[2 * i : 2 * i + 2]])[0] for i in range(n // 2)]
-                if n % 2 == 1:
-                    (new_layer[-1],) = or_ @ builder[new_layer[-1], layer[-1]]
-                layer = new_layer
-            assert len(layer) == 1
-            bit_1 @ builder[layer[0]]
+        builder.add_inputs(bc.bits(self._n))
+        for clause in self._clauses:
+            self._add_clause(builder, clause)
         return builder.diagram()
 
+    @staticmethod
+    def _add_clause(builder: DiagramBuilder, clause: Clause) -> None:
+        """NOT gates for the negative literals, a balanced tree of OR gates, ``bit_1`` on its root."""
+        level: list[Wire] = []
+        for lit in clause:
+            level.append(lit - 1 if lit > 0 else (bc.not_ @ builder[-lit - 1])[0])
+        while len(level) > 1:
+            pairs = len(level) // 2
+            merged = [(bc.or_ @ builder[level[2 * p], level[2 * p + 1]])[0] for p in range(pairs)]
+            if len(level) % 2:
+                merged[-1] = (bc.or_ @ builder[merged[-1], level[-1]])[0]
+            level = merged
+        bc.bit_1 @ builder[level[0]]
+
+    def contraction_wiring(self, *, mode: str = "bintree") -> Wiring:
+        """The wiring shared by ``inputs(x) >> diagram()`` for every ``x`` (``sat.py:231-246``)."""
+        return (self.inputs(0) >> self.diagram(mode=mode)).flatten().wiring
+
     def __repr__(self) -> str:
-        attrs = [f"{self.num_vars} vars", f"{len(self.clauses)} clauses"]
-        ks = {len(clause) for clause in self.clauses}
-        attrs.append(f"k={ks.pop()}" if len(ks) == 1 else f"k in [{min(ks)}..{max(ks)}]")
-        return f"<CNFInstance: {', '.join(attrs)}>"
+        sizes = sorted({len(clause) for clause in self._clauses})
+        k = f"k={sizes[0]}" if len(sizes) == 1 else f"k in [{sizes[0]}..{sizes[-1]}]"
+        return f"<CNFInstance: {self._n} vars, {len(self._clauses)} clauses, {k}>"
