@@ -376,6 +376,10 @@ inline void permute_bits(tsb_ctx* ctx, const void* src, const BitLabels& src_bit
   launch_generic(ctx, g, src, nullptr, dst, stream);
 }
 
+// Summed wires handled inside one merge launch; more are split off into a temporary leading axis of the
+// result and summed by further passes, so that the work stays parallel over the output (split-K).
+constexpr int kSplitKBits = 8;
+
 // ---- merge lowering -------------------------------------------------------------------------
 struct MergeArgs {
   MergeDesc d;

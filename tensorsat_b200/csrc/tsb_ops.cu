@@ -68,7 +68,7 @@ struct GemmShape {
 };
 
 GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& ob, int out_elem_size,
-                     double min_intensity) {
+                     double min_intensity, bool boolean_operands) {
   GemmShape g;
   std::set<int64_t> sl(lb.begin(), lb.end()), sr(rb.begin(), rb.end()), so(ob.begin(), ob.end());
   for (auto x : ob) {
@@ -88,7 +88,8 @@ GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& 
   int m = (int)g.M.size(), n = (int)g.N.size();
   const int k = (int)g.K.size(), b = (int)g.B.size();
   if (m < n) { std::swap(g.M, g.N); std::swap(m, n); g.swap = true; }
-  if (m < 7 || n < 5 || k < 5 || k > 15) return g;
+  // s32 accumulation is exact for 0/1 operands up to K = 2^24, for general u8 operands up to K = 2^15
+  if (m < 7 || n < 5 || k < 5 || k > (boolean_operands ? 24 : 15)) return g;
   const double ops = 2.0 * std::exp2((double)(b + m + n + k));
   const double bytes = std::exp2((double)(b + m + k)) + std::exp2((double)(b + n + k)) +
                        out_elem_size * std::exp2((double)(b + m + n));
@@ -155,16 +156,18 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
   const int64_t n_out = numel(oe.data(), out_rank);
 
   // ---- fast path: binary extents, monotone merge (with operand permutes when needed)
-  bool fast = !force_generic && all_pow2(le.data(), lhs_rank) && all_pow2(re.data(), rhs_rank) && n_out >= 256 &&
-              ((((uintptr_t)lhs | (uintptr_t)rhs | (uintptr_t)out) & 15) == 0);
-  if (fast) {
+  const bool binary = !force_generic && all_pow2(le.data(), lhs_rank) && all_pow2(re.data(), rhs_rank) &&
+                      ((((uintptr_t)lhs | (uintptr_t)rhs | (uintptr_t)out) & 15) == 0);
+  bool fast = binary && n_out >= 256;
+  if (binary) {
     BitLabels lb = bit_labels(lhs_wires, lhs_rank, wext), rb = bit_labels(rhs_wires, rhs_rank, wext),
               ob = bit_labels(out_wires, out_rank, wext);
-    if (has_dups(lb) || has_dups(rb) || has_dups(ob)) fast = false;
+    const bool dups = has_dups(lb) || has_dups(rb) || has_dups(ob);
+    if (dups) fast = false;
 #ifndef TSB_HOST_EMU
     // ---- tensor cores: steps above the ridge go through transpose -> int8 GEMM -> transpose
     if (fast && !accumulate && dl == TSB_U8 && dr == TSB_U8 && (clamp ? dout == TSB_U8 : dout != TSB_U8)) {
-      GemmShape g = gemm_shape(lb, rb, ob, dtype_size(dout), 64.0);
+      GemmShape g = gemm_shape(lb, rb, ob, dtype_size(dout), 64.0, clamp);
       if (g.ok) {
         const void* pa = g.swap ? rhs : lhs;
         const void* pb = g.swap ? lhs : rhs;
@@ -214,6 +217,37 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
       }
     }
 #endif
+    if (!dups && !accumulate) {
+      // ---- split-K: more than kSplitKBits summed labels -> keep the upper ones as leading result axes,
+      // then sum them away pass by pass (each pass is a merge against the scalar 1)
+      std::set<int64_t> oset(ob.begin(), ob.end()), lset(lb.begin(), lb.end()), rset(rb.begin(), rb.end());
+      BitLabels ks;
+      for (auto x : lb) if (!oset.count(x)) ks.push_back(x);
+      for (auto x : rb) if (!oset.count(x) && !lset.count(x)) ks.push_back(x);
+      if ((int)ks.size() > kSplitKBits) {
+        BitLabels keep(ks.begin(), ks.begin() + ((int)ks.size() - kSplitKBits));  // most significant summed labels
+        BitLabels tb = keep;
+        tb.insert(tb.end(), ob.begin(), ob.end());
+        if (tb.size() <= 40) {
+          const int tdt = clamp ? TSB_U8 : dout;
+          Temp tmp(ctx, (size_t)dtype_size(tdt) << tb.size());
+          // labels -> fresh wire ids for the recursive calls (one wire per bit label)
+          std::map<int64_t, int32_t> id;
+          auto wires_of = [&](const BitLabels& b) {
+            std::vector<int32_t> w;
+            for (auto x : b) { auto it = id.find(x); if (it == id.end()) it = id.emplace(x, (int32_t)id.size()).first; w.push_back(it->second); }
+            return w;
+          };
+          std::vector<int32_t> wl = wires_of(lb), wr = wires_of(rb), wt = wires_of(tb), wo = wires_of(ob);
+          std::vector<int32_t> ext(id.size(), 2);
+          contract2_impl(ctx, lhs, (int)wl.size(), wl.data(), dl, rhs, (int)wr.size(), wr.data(), dr, tmp.p, (int)wt.size(),
+                         wt.data(), tdt, (int)ext.size(), ext.data(), mode, false, false, stream);
+          contract2_impl(ctx, tmp.p, (int)wt.size(), wt.data(), tdt, ctx->d_one, 0, nullptr, TSB_U8, out, (int)wo.size(),
+                         wo.data(), dout, (int)ext.size(), ext.data(), mode, false, false, stream);
+          return;
+        }
+      }
+    }
     if (fast) {
       MergeArgs m = make_merge_desc(lb, &rb, ob, accumulate);
       std::unique_ptr<Temp> tl, tr;

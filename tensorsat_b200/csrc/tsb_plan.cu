@@ -32,7 +32,8 @@ struct GemmShape {
   bool swap = false;
   BitLabels B, M, N, K;
 };
-GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& ob, int out_elem_size, double min_intensity);
+GemmShape gemm_shape(const BitLabels& lb, const BitLabels& rb, const BitLabels& ob, int out_elem_size, double min_intensity,
+                     bool boolean_operands);
 GenDesc lower_generic_contract(int lhs_rank, const int32_t* lhs_wires, int rhs_rank, const int32_t* rhs_wires,
                                int out_rank, const int32_t* out_wires, const int32_t* wext, int dl, int dr, int dout,
                                bool clamp, bool accumulate, bool& out_dups);
@@ -440,9 +441,10 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         // steps above the ridge are lowered at run time by contract2_impl (transpose -> tcgen05 GEMM -> transpose)
         if (!(P.flags & TSB_PLAN_NO_GEMM) && P.nodes[op.lhs].dtype == TSB_U8 && P.nodes[op.rhs].dtype == TSB_U8 &&
             (clamp ? o.dtype == TSB_U8 : o.dtype != TSB_U8) && !(op.per_slice && op.out == P.root))
-          to_gemm = gemm_shape(lb, rb, ob, dtype_size(o.dtype), 64.0).ok;
+          to_gemm = gemm_shape(lb, rb, ob, dtype_size(o.dtype), 64.0, clamp).ok;
 #endif
         MergeArgs m = make_merge_desc(lb, &rb, ob, false);
+        if (m.ok && m.d.kbits > kSplitKBits && !(op.per_slice && op.out == P.root)) to_gemm = true;  // run-time split-K
         if (to_gemm) {
           op.use_gemm = true;
         } else if (m.ok) {
@@ -450,6 +452,15 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
           op.md = m.d;
         }
       }
+    }
+    if (op.kind == OP_STEP && !force_generic && !op.use_merge && !op.use_gemm && !(op.per_slice && op.out == P.root)) {
+      // many summed wires but too few outputs for the merge kernel: run-time lowering splits the sum
+      std::set<int32_t> so(op.ow.begin(), op.ow.end());
+      double kb = 0;
+      bool pow2 = true;
+      for (auto w : op.lw) { pow2 = pow2 && is_pow2(P.wext[w]); if (!so.count(w)) kb += std::log2((double)P.wext[w]); }
+      for (auto w : op.rw) pow2 = pow2 && is_pow2(P.wext[w]);
+      if (pow2 && kb > 12) op.use_gemm = true;
     }
     if (op.use_merge || op.use_gemm) continue;
     // generic kernel: lowered once, here (the root of a sliced plan accumulates and stays on the slow path)
@@ -697,7 +708,11 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
   const bool clamp = P.mode == TSB_SAT;
   int dout = o.dtype;
   if (P.stack_out && op.out == P.root) dout = P.nodes[P.rnode].dtype;
-  if (op.use_merge && (((uintptr_t)pl | (uintptr_t)pr | (uintptr_t)po) & 15) == 0) {
+  // each operand only has to be aligned to the vector it is loaded with (slices of tiny shared tensors
+  // start at multiples of their own size), the result to 16 bytes
+  const uintptr_t al = ((uintptr_t)dtype_size(a.dtype) << __builtin_popcount((unsigned)op.md.nibL)) - 1;
+  const uintptr_t ar = ((uintptr_t)dtype_size(b.dtype) << __builtin_popcount((unsigned)op.md.nibR)) - 1;
+  if (op.use_merge && ((uintptr_t)pl & al) == 0 && ((uintptr_t)pr & ar) == 0 && ((uintptr_t)po & 15) == 0) {
     MergeDesc d = op.md;
     d.accumulate = acc ? 1 : 0;
     launch_merge(ctx, d, pl, a.dtype, pr, b.dtype, po, dout, clamp, stream);

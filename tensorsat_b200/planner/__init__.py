@@ -1,6 +1,7 @@
 """Host-side planning: flat networks, contraction trees, slicing (not on the timed path)."""
 
 from .network import Network
+from .sampling import fix_wires, sample_subcube
 from .search import find_tree
 from .tree import ContractionTree, TreeStats, linear_to_ssa, ssa_to_linear
 
@@ -9,6 +10,8 @@ __all__ = [
     "ContractionTree",
     "TreeStats",
     "find_tree",
+    "fix_wires",
+    "sample_subcube",
     "linear_to_ssa",
     "ssa_to_linear",
 ]

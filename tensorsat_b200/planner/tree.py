@@ -228,6 +228,35 @@ class ContractionTree:
             tree = best[1]
         return tree
 
+    def slice_to_fast(self, target_log2_size: float, *, max_sliced: int = 4096) -> "ContractionTree":
+        """Slicing for very wide trees (hundreds of sliced wires): each round slices the non-output wire
+        that carries the most weight, where a wire's weight is the summed size of the intermediates above
+        the target that hold it.  One pass over the steps per round instead of one tree rebuild per candidate."""
+        out = set(self.network.output)
+        lg = [math.log2(d) for d in self.network.size_dict]
+        sliced: list[int] = list(self.sliced_wires)
+        sets = [set(st.out_wires) for st in self.steps]
+        while True:
+            weight: dict[int, float] = {}
+            worst = 0.0
+            for ws in sets:
+                sz = sum(lg[w] for w in ws)
+                worst = max(worst, sz)
+                if sz > target_log2_size + 1e-9:
+                    bonus = 2.0 ** min(sz - target_log2_size, 60.0)
+                    for w in ws:
+                        if w not in out:
+                            weight[w] = weight.get(w, 0.0) + bonus
+            if worst <= target_log2_size + 1e-9:
+                break
+            if not weight or len(sliced) >= max_sliced:
+                raise ValueError("Slicing budget exhausted before reaching the target size.")
+            w = max(sorted(weight), key=lambda x: weight[x])
+            sliced.append(w)
+            for ws in sets:
+                ws.discard(w)
+        return self.with_sliced(sliced)
+
     # -- serialisation -----------------------------------------------------------
     def to_json(self) -> dict[str, Any]:
         return {

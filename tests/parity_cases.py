@@ -189,6 +189,25 @@ def test_counting_merge_int32_kernels(tl, tr):
         assert np.array_equal(Od.cpu().numpy().reshape((2,) * R).astype(np.int64), want)
 
 
+@pytest.mark.parametrize("k,r", [(9, 0), (13, 0), (14, 2), (12, 5), (17, 1)])
+def test_contract2_many_summed_wires(k, r):
+    """Dot-product-like steps (many summed wires, few outputs) are split over the summed wires (split-K)."""
+    if k + r > SCALE["big_bits"] + 3:
+        pytest.skip("too large for the emulated build")
+    rng = np.random.default_rng(k * 10 + r)
+    kw, ow = list(range(k)), list(range(k, k + r))
+    lw = [int(w) for w in rng.permutation(kw + ow[: (r + 1) // 2])]
+    rw = [int(w) for w in rng.permutation(kw + ow[(r + 1) // 2:])]
+    lhs = _rand01(rng, (2,) * len(lw), 0.02)
+    rhs = _rand01(rng, (2,) * len(rw), 0.02)
+    got = CudaFinRel.contract2(CudaFinRel(lhs), lw, CudaFinRel(rhs), rw, ow)
+    want = O.contract2(lhs, lw, rhs, rw, ow)
+    assert np.array_equal(got.tensor, want)
+    dense_l, dense_r = _rand01(rng, (2,) * len(lw), 0.5), _rand01(rng, (2,) * len(rw), 0.5)
+    gotc = CudaCountRel.contract2(CudaCountRel(dense_l), lw, CudaCountRel(dense_r), rw, ow)
+    assert np.array_equal(gotc.tensor, O.contract2(dense_l, lw, dense_r, rw, ow, mode="count"))
+
+
 def test_contract2_validation_errors():
     a, b = CudaFinRel(np.ones((2, 2), np.uint8)), CudaFinRel(np.ones((2,), np.uint8))
     with pytest.raises(ValueError):
