@@ -176,6 +176,10 @@ inline GenDesc make_gen_desc(std::vector<LDim> dims, int dl, int dr, int dout, b
 
 inline void launch_generic(tsb_ctx* ctx, const GenDesc& g, const void* lhs, const void* rhs, void* out,
                            cudaStream_t stream) {
+  // the generic kernel is the slow, fully general path: refuse work that would run for minutes
+  TSB_CHECK((double)g.n_out_iter * (double)g.n_red_iter <= 68719476736.0 /* 2^36 */, TSB_ERR_UNSUPPORTED,
+            "step with %lld outputs x %lld summed terms has no fast kernel (non-binary extents or repeated wires?)",
+            (long long)g.n_out_iter, (long long)g.n_red_iter);
   const int grid = grid_for(ctx, g.n_out_iter, 256);
   TSB_LAUNCH(k_generic, dim3(grid), dim3(256), 0, stream, g, lhs, rhs, out);
   ctx->launches++;
@@ -379,6 +383,10 @@ inline void permute_bits(tsb_ctx* ctx, const void* src, const BitLabels& src_bit
 // Summed wires handled inside one merge launch; more are split off into a temporary leading axis of the
 // result and summed by further passes, so that the work stays parallel over the output (split-K).
 constexpr int kSplitKBits = 8;
+// Arithmetic intensity (ops per algorithmic byte) above which a step goes to the tensor cores: measured on
+// B200 the CUDA-core merge kernel needs about 0.1 ms per summed-wire combination and 2^30 outputs, the
+// transposes around the GEMM about 0.8 ms per 2^30 outputs, so K >= 32 with wide M, N is the break-even.
+constexpr double kGemmMinIntensity = 48.0;
 
 // ---- merge lowering -------------------------------------------------------------------------
 struct MergeArgs {

@@ -167,7 +167,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
 #ifndef TSB_HOST_EMU
     // ---- tensor cores: steps above the ridge go through transpose -> int8 GEMM -> transpose
     if (fast && !accumulate && dl == TSB_U8 && dr == TSB_U8 && (clamp ? dout == TSB_U8 : dout != TSB_U8)) {
-      GemmShape g = gemm_shape(lb, rb, ob, dtype_size(dout), 64.0, clamp);
+      GemmShape g = gemm_shape(lb, rb, ob, dtype_size(dout), kGemmMinIntensity, clamp);
       if (g.ok) {
         const void* pa = g.swap ? rhs : lhs;
         const void* pb = g.swap ? lhs : rhs;
@@ -217,7 +217,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
       }
     }
 #endif
-    if (!dups && !accumulate) {
+    if (!dups) {
       // ---- split-K: more than kSplitKBits summed labels -> keep the upper ones as leading result axes,
       // then sum them away pass by pass (each pass is a merge against the scalar 1)
       std::set<int64_t> oset(ob.begin(), ob.end()), lset(lb.begin(), lb.end()), rset(rb.begin(), rb.end());
@@ -228,7 +228,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
         BitLabels keep(ks.begin(), ks.begin() + ((int)ks.size() - kSplitKBits));  // most significant summed labels
         BitLabels tb = keep;
         tb.insert(tb.end(), ob.begin(), ob.end());
-        if (tb.size() <= 40) {
+        if ((size_t)(clamp ? 1 : dtype_size(dout)) << std::min<size_t>(tb.size(), 40) <= ((size_t)1 << 34) && tb.size() <= 34) {
           const int tdt = clamp ? TSB_U8 : dout;
           Temp tmp(ctx, (size_t)dtype_size(tdt) << tb.size());
           // labels -> fresh wire ids for the recursive calls (one wire per bit label)
@@ -243,7 +243,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
           contract2_impl(ctx, lhs, (int)wl.size(), wl.data(), dl, rhs, (int)wr.size(), wr.data(), dr, tmp.p, (int)wt.size(),
                          wt.data(), tdt, (int)ext.size(), ext.data(), mode, false, false, stream);
           contract2_impl(ctx, tmp.p, (int)wt.size(), wt.data(), tdt, ctx->d_one, 0, nullptr, TSB_U8, out, (int)wo.size(),
-                         wo.data(), dout, (int)ext.size(), ext.data(), mode, false, false, stream);
+                         wo.data(), dout, (int)ext.size(), ext.data(), mode, accumulate, false, stream);
           return;
         }
       }

@@ -441,10 +441,10 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         // steps above the ridge are lowered at run time by contract2_impl (transpose -> tcgen05 GEMM -> transpose)
         if (!(P.flags & TSB_PLAN_NO_GEMM) && P.nodes[op.lhs].dtype == TSB_U8 && P.nodes[op.rhs].dtype == TSB_U8 &&
             (clamp ? o.dtype == TSB_U8 : o.dtype != TSB_U8) && !(op.per_slice && op.out == P.root))
-          to_gemm = gemm_shape(lb, rb, ob, dtype_size(o.dtype), 64.0, clamp).ok;
+          to_gemm = gemm_shape(lb, rb, ob, dtype_size(o.dtype), kGemmMinIntensity, clamp).ok;
 #endif
         MergeArgs m = make_merge_desc(lb, &rb, ob, false);
-        if (m.ok && m.d.kbits > kSplitKBits && !(op.per_slice && op.out == P.root)) to_gemm = true;  // run-time split-K
+        if (m.ok && m.d.kbits > kSplitKBits) to_gemm = true;  // run-time split-K
         if (to_gemm) {
           op.use_gemm = true;
         } else if (m.ok) {
@@ -453,7 +453,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         }
       }
     }
-    if (op.kind == OP_STEP && !force_generic && !op.use_merge && !op.use_gemm && !(op.per_slice && op.out == P.root)) {
+    if (op.kind == OP_STEP && !force_generic && !op.use_merge && !op.use_gemm) {
       // many summed wires but too few outputs for the merge kernel: run-time lowering splits the sum
       std::set<int32_t> so(op.ow.begin(), op.ow.end());
       double kb = 0;
@@ -479,7 +479,8 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     }
     if (op.has_gd && !op.per_slice && !(P.n_leaves == 1 && sliced_any)) {
       const GenDesc& g = op.gd;
-      bool ok = g.n_free + g.n_red <= kSmallMaxDims && g.n_out_iter <= (1 << 14) && g.n_red_iter <= (1 << 12);
+      bool ok = g.n_free + g.n_red <= kSmallMaxDims && g.n_out_iter <= (1 << 14) && g.n_red_iter <= (1 << 12) &&
+                g.n_out_iter * g.n_red_iter <= (1 << 17);  // one CTA of 64 threads: keep it in the microsecond range
       for (int q = 0; ok && q < g.n_free + g.n_red; q++)
         ok = g.sl[q] < (int64_t(1) << 30) && g.sr[q] < (int64_t(1) << 30) && g.so[q] < (int64_t(1) << 30);
       op.small = ok;

@@ -79,3 +79,34 @@ def test_contract2_above_the_ridge_uses_tensor_cores_and_matches_oracle(seed):
     assert np.array_equal(got.tensor, want) and 0 < want.sum() < want.size
     gotc = CudaCountRel.contract2(CudaCountRel(lhs), lw, CudaCountRel(rhs), rw, ow)
     assert np.array_equal(gotc.tensor, O.contract2(lhs, lw, rhs, rw, ow, mode="count"))
+
+
+@pytest.mark.parametrize("mode", ["sat", "count"])
+def test_plan_with_a_step_above_the_ridge(mode):
+    """A three-tensor network whose first step is GEMM-shaped (m=9, n=7, k=6): inside a plan the step is lowered
+    at run time to transpose -> tcgen05 GEMM -> transpose; the result must equal the oracle's."""
+    import numpy as np
+    import torch
+
+    from oracle import fin_rel_oracle as O
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(5)
+    M, N, K = list(range(0, 9)), list(range(9, 16)), list(range(16, 22))
+    inputs = [tuple(int(w) for w in rng.permutation(M + K)), tuple(int(w) for w in rng.permutation(N + K)),
+              tuple(M[:4] + N[:3])]
+    dens = (0.03, 0.3, 0.5) if mode == "sat" else (0.5, 0.5, 0.5)
+    leaves = [(rng.random((2,) * len(ws)) < p).astype(np.uint8) for ws, p in zip(inputs, dens)]
+    out = tuple(M[6:] + N[5:])
+    path = [(0, 1), (3, 2)]
+    code = _native.MODE_SAT if mode == "sat" else _native.MODE_COUNT
+    plan = _native.Plan(inputs, out, [2] * 22, path, (), mode=code)
+    kinds = [o["kind"] for o in plan.describe()["ops"]]
+    assert "gemm" in kinds
+    dev = [_native.upload(t) for t in leaves]
+    res = _native.empty(plan.info["out_numel"], code)
+    plan.execute(dev, res)
+    torch.cuda.synchronize()
+    want = O.execute_tree(inputs, out, leaves, path, mode=mode)
+    assert np.array_equal(res.cpu().numpy().reshape(want.shape), want)
+    assert 0 < np.count_nonzero(want) 
