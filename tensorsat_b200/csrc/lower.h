@@ -512,6 +512,10 @@ template <> void launch_merge_cnt_t<uint8_t, int32_t>(tsb_ctx*, const MergeDesc&
 template <> void launch_merge_cnt_t<int32_t, uint8_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
 template <> void launch_merge_cnt_t<int32_t, int32_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
 
+bool merge_wide_supported(const MergeDesc& d, const void* l, int dl, const void* r, int dr, const void* o);
+void launch_merge_wide(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
+                       cudaStream_t s);
+
 inline void launch_merge(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,
                          int dout, bool clamp, cudaStream_t s) {
   if (clamp && dl == TSB_U8 && dr == TSB_U8 && dout == TSB_U8 && merge_sat_supported(d)) {
@@ -524,6 +528,10 @@ inline void launch_merge(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl
     else if (dl == TSB_U8) launch_merge_cnt_t<uint8_t, int32_t>(ctx, d, l, r, o, s);
     else if (dr == TSB_U8) launch_merge_cnt_t<int32_t, uint8_t>(ctx, d, l, r, o, s);
     else launch_merge_cnt_t<int32_t, int32_t>(ctx, d, l, r, o, s);
+    return;
+  }
+  if (!clamp && dout == TSB_I64 && merge_wide_supported(d, l, dl, r, dr, o)) {
+    launch_merge_wide(ctx, d, l, dl, r, dr, o, s);  // counting semiring, int64 results
     return;
   }
   launch_merge_generic(ctx, d, l, dl, r, dr, o, dout, clamp, s);

@@ -189,6 +189,36 @@ def test_counting_merge_int32_kernels(tl, tr):
         assert np.array_equal(Od.cpu().numpy().reshape((2,) * R).astype(np.int64), want)
 
 
+@pytest.mark.parametrize("tl", ["u8", "i32", "i64"])
+@pytest.mark.parametrize("tr", ["u8", "i32", "i64"])
+def test_counting_merge_int64_kernel(tl, tr):
+    """The int64-result counting kernel (two outputs per thread) through tsb_contract2, all nine operand type pairs,
+    with 0..3 summed wires and random lane masks."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(12)
+    dt = {"u8": (np.uint8, 4), "i32": (np.int32, 1 << 20), "i64": (np.int64, 1 << 38)}
+    for trial in range(5):
+        R = int(rng.integers(6, SCALE["big_bits"] - 2))
+        nk = trial % 4
+        out_w = list(range(nk, R + nk))
+        ks = list(range(nk))
+        lw = ks + sorted(int(w) for w in rng.choice(out_w, size=int(rng.integers(1, R)), replace=False))
+        rest = [w for w in out_w if w not in lw]
+        rw = ks[: max(0, nk - trial % 2)] + sorted(set(rest) | set(int(w) for w in rng.choice(out_w, size=int(rng.integers(1, R)), replace=False)))
+        hi_r = dt[tr][1] if tl != "i64" else min(dt[tr][1], 1 << 20)      # keep products inside int64
+        L = rng.integers(0, dt[tl][1], size=(2,) * len(lw)).astype(dt[tl][0])
+        Rr = rng.integers(0, hi_r, size=(2,) * len(rw)).astype(dt[tr][0])
+        dev = _native.device()
+        Ld, Rd = torch.from_numpy(L.reshape(-1)).to(dev), torch.from_numpy(Rr.reshape(-1)).to(dev)
+        Od = torch.empty(1 << R, dtype=torch.int64, device=dev)
+        _native.contract2(Ld, [2] * len(lw), lw, Rd, [2] * len(rw), rw, Od, [2] * R, out_w, 1)
+        want = O.einsum2(L.astype(np.int64), lw, Rr.astype(np.int64), rw, out_w)
+        assert np.array_equal(Od.cpu().numpy().reshape((2,) * R), want)
+
+
 @pytest.mark.parametrize("k,r", [(9, 0), (13, 0), (14, 2), (12, 5), (17, 1)])
 def test_contract2_many_summed_wires(k, r):
     """Dot-product-like steps (many summed wires, few outputs) are split over the summed wires (split-K)."""

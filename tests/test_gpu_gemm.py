@@ -92,15 +92,17 @@ def test_plan_with_a_step_above_the_ridge(mode):
     from tensorsat_b200 import _native
 
     rng = np.random.default_rng(5)
-    M, N, K = list(range(0, 9)), list(range(9, 16)), list(range(16, 22))
+    # counting mode stores the step's output as uint8 while its bound fits 7 bits: 8 summed wires make it int32
+    nk = 6 if mode == "sat" else 8
+    M, N, K = list(range(0, 9)), list(range(9, 16)), list(range(16, 16 + nk))
     inputs = [tuple(int(w) for w in rng.permutation(M + K)), tuple(int(w) for w in rng.permutation(N + K)),
               tuple(M[:4] + N[:3])]
-    dens = (0.03, 0.3, 0.5) if mode == "sat" else (0.5, 0.5, 0.5)
+    dens = (0.01, 0.1, 0.02) if mode == "sat" else (0.5, 0.5, 0.5)
     leaves = [(rng.random((2,) * len(ws)) < p).astype(np.uint8) for ws, p in zip(inputs, dens)]
-    out = tuple(M[6:] + N[5:])
+    out = tuple(M[4:] + N[3:])   # every M, N wire outlives the first step, the six K wires are summed there
     path = [(0, 1), (3, 2)]
     code = _native.MODE_SAT if mode == "sat" else _native.MODE_COUNT
-    plan = _native.Plan(inputs, out, [2] * 22, path, (), mode=code)
+    plan = _native.Plan(inputs, out, [2] * (16 + nk), path, (), mode=code)
     kinds = [o["kind"] for o in plan.describe()["ops"]]
     assert "gemm" in kinds
     dev = [_native.upload(t) for t in leaves]
