@@ -180,6 +180,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pack", action="store_true", help="keep boolean intermediates at one byte per entry (A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
@@ -204,7 +205,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cnf, diagram, tree = load_tree()
-    contraction = TreeContraction(CudaFinRel, diagram.wiring, tree=tree)
+    contraction = TreeContraction(CudaFinRel, diagram.wiring, tree=tree, bit_packing=not args.no_pack)
     plan = contraction.plan()
     n_slices = plan.info["n_slices"]
     lo, hi = slice_block(n_slices, rank, world)
@@ -277,22 +278,26 @@ def main() -> None:
         plan.set_timing(False)
         peak, peak_src = hbm_peak()
         share = (hi - lo) if n_slices > 1 else 1
-        # dominant kernel: the per-slice k_merge_sat launches (the large middle of the tree)
-        merge = [o for o in desc["ops"] if o["kind"] == "merge" and (o["per_slice"] or n_slices == 1)]
+        # dominant kernel: the per-slice merge launches (the large middle of the tree); k_merge_bits when the plan
+        # runs them bit-packed (bytes = 1/8 per entry, the representation the kernel actually moves), else k_merge_sat
+        packed = plan.info["n_packed_steps"] > 0
+        kind = "bits" if packed else "merge"
+        merge = [o for o in desc["ops"] if o["kind"] == kind and (o["per_slice"] or n_slices == 1)]
         mbytes = sum(o["bytes"] * (share if o["per_slice"] else 1) for o in merge)
         mms = sum(o["ms"] for o in merge)
         all_ms = sum(o["ms"] for o in desc["ops"])
         n_launch = sum((share if o["per_slice"] else 1) for o in merge)
         achieved = mbytes / (mms * 1e-3) / 1e9 if mms > 0 else 0.0
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "merge_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "bits_traffic.json" if packed else "merge_traffic.json")
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
                     traffic = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_merge_sat<NIBL,NIBR> (per-slice launches)", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": ("k_merge_bits" if packed else "k_merge_sat<NIBL,NIBR>") + " (per-slice launches)",
+                "bytes_per_entry": 0.125 if packed else 1, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": mbytes / max(n_launch, 1), "avg_launch_ms": mms / max(n_launch, 1),
                 "launches_per_step": n_launch, "share_of_step": mms / all_ms if all_ms else None,
@@ -310,7 +315,9 @@ def main() -> None:
             "config": {"workload": WORKLOAD, "n_slices": int(n_slices), "slices_per_rank": int(hi - lo),
                        "verdict": "SAT" if verdict else "UNSAT", "l2": "inputs larger than L2",
                        "peak_arena_bytes": int(plan.info["peak_bytes"]), "kernels_per_step": launches // max(args.steps, 1),
-                       "alg_bytes_per_step": plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n_slices},
+                       "alg_bytes_per_step": plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n_slices,
+                       "alg_bytes_per_step_at_1B_per_entry": plan.info["alg_bytes_u8_shared"] + plan.info["alg_bytes_u8_per_slice"] * n_slices,
+                       "bit_packed_steps": int(plan.info["n_packed_steps"]), "conversions": int(plan.info["n_conversions"])},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": contraction.h2d_bytes,
                     "d2h_bytes_per_step": contraction.d2h_bytes},

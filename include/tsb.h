@@ -126,6 +126,25 @@ int tsb_fill(tsb_ctx* ctx, void* dst, int64_t n, int64_t value, int dtype, tsb_s
 int tsb_convert(tsb_ctx* ctx, const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
                 int clamp, tsb_stream stream);
 
+/* ---- bit-packed boolean relations (1 bit per entry; the reference authors' planned "Binary Packing",
+ *      paper/typst/main.typ:336-339) ------------------------------------------------
+ * Entry i of a packed tensor is bit (i & 31) of 32-bit word (i >> 5); a packed buffer holds
+ * max(16, ceil(n / 8)) bytes and is 16-byte aligned.  Plans use this representation internally for the
+ * large steps of a TSB_SAT contraction (tsb_plan_info_t.n_packed_steps); these three entry points expose
+ * the same kernels. */
+/* dst bit i = (src[i] != 0); src holds n uint8 entries. */
+int tsb_pack_bits(tsb_ctx* ctx, const void* src_u8, void* dst_bits, int64_t n, tsb_stream stream);
+/* dst[i] = bit i of src (accumulate != 0: dst[i] |= bit i). */
+int tsb_unpack_bits(tsb_ctx* ctx, const void* src_bits, void* dst_u8, int64_t n, int accumulate,
+                    tsb_stream stream);
+/* FinRel._contract2 (tensorsat/lang/fin_rel.py:255-288) with lhs, rhs and out all bit-packed, boolean
+ * semiring.  All extents must be 2, the kept wires must appear in the same relative order in lhs, rhs and
+ * out with the summed wires leading (the layout plans use), out_rank >= 7 and at most 8 summed wires;
+ * anything else returns TSB_ERR_UNSUPPORTED. */
+int tsb_contract2_bits(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* lhs_wires,
+                       const void* rhs, int rhs_rank, const int32_t* rhs_wires, void* out, int out_rank,
+                       const int32_t* out_wires, int n_wires, const int32_t* wire_extents, tsb_stream stream);
+
 /* result = 1 iff every one of the n elements equals 1.  Synchronises the stream. */
 int tsb_all_ones(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result,
                  tsb_stream stream);
@@ -155,6 +174,7 @@ typedef struct {
 #define TSB_PLAN_NO_GRAPH 1u     /* launch kernels directly instead of replaying a CUDA graph */
 #define TSB_PLAN_FORCE_GENERIC 2u /* use only the generic kernel (parity reference on device) */
 #define TSB_PLAN_NO_GEMM 4u      /* never lower a step to the tcgen05 GEMM */
+#define TSB_PLAN_NO_PACK 8u      /* keep every boolean intermediate at one byte per entry (no bit-packing) */
 
 typedef struct {
   int64_t n_slices;
@@ -170,6 +190,10 @@ typedef struct {
   double alg_ops_per_slice;
   int32_t log2_max_tensor;    /* elements, largest intermediate of one slice */
   int32_t may_overflow;       /* counting bound exceeds int64 */
+  double alg_bytes_u8_shared;    /* the same steps at one byte per boolean entry (SURVEY.md §8d's definition); */
+  double alg_bytes_u8_per_slice; /* alg_bytes_* count the representation the plan uses (1/8 byte when bit-packed) */
+  int32_t n_packed_steps;     /* steps executed on bit-packed operands */
+  int32_t n_conversions;      /* byte <-> bit conversion launches (per execution of every op once) */
 } tsb_plan_info_t;
 
 int tsb_plan_create(tsb_ctx* ctx, const tsb_plan_desc* desc, tsb_plan** plan);

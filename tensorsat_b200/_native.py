@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtsb.so")
 
 TSB_U8, TSB_I32, TSB_I64 = 0, 1, 2
 MODE_SAT, MODE_COUNT = 0, 1
-PLAN_NO_GRAPH, PLAN_FORCE_GENERIC, PLAN_NO_GEMM = 1, 2, 4
+PLAN_NO_GRAPH, PLAN_FORCE_GENERIC, PLAN_NO_GEMM, PLAN_NO_PACK = 1, 2, 4, 8
 
 _STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: MemoryError, 4: NotImplementedError, 5: OverflowError}
 
@@ -73,6 +73,10 @@ class PlanInfo(C.Structure):
         ("alg_ops_per_slice", C.c_double),
         ("log2_max_tensor", C.c_int32),
         ("may_overflow", C.c_int32),
+        ("alg_bytes_u8_shared", C.c_double),
+        ("alg_bytes_u8_per_slice", C.c_double),
+        ("n_packed_steps", C.c_int32),
+        ("n_conversions", C.c_int32),
     ]
 
 
@@ -82,7 +86,7 @@ EXPORTS = [
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
     "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
     "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",
-    "tsb_plan_destroy", "tsb_gemm_u8",
+    "tsb_plan_destroy", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
 ]
 """Every symbol include/tsb.h declares (checked by tests/test_abi.py)."""
 
@@ -250,6 +254,28 @@ def fill(out: Any, value: int, mode: int) -> None:
 def widen(src: Any, out: Any) -> None:
     _check(lib().tsb_convert(ctx(), _ptr(src), dtype_code(src), _ptr(out), dtype_code(out), C.c_int64(src.numel()), 0,
                              stream()))
+
+
+def packed_nbytes(n_entries: int) -> int:
+    """Bytes of a bit-packed buffer of ``n_entries`` boolean entries (include/tsb.h)."""
+    return max(16, (int(n_entries) + 7) // 8)
+
+
+def pack_bits(src: Any, dst: Any) -> None:
+    """``dst`` bit i = ``src[i] != 0`` (``src`` uint8, ``dst`` a uint8 buffer of ``packed_nbytes`` bytes)."""
+    _check(lib().tsb_pack_bits(ctx(), _ptr(src), _ptr(dst), C.c_int64(src.numel()), stream()))
+
+
+def unpack_bits(src: Any, dst: Any, accumulate: bool = False) -> None:
+    _check(lib().tsb_unpack_bits(ctx(), _ptr(src), _ptr(dst), C.c_int64(dst.numel()), int(bool(accumulate)), stream()))
+
+
+def contract2_bits(lhs: Any, lhs_wires: Sequence[int], rhs: Any, rhs_wires: Sequence[int], out: Any,
+                   out_wires: Sequence[int], n_wires: int) -> None:
+    """Boolean ``_contract2`` on three bit-packed buffers (all wires of extent 2, one wire order)."""
+    _check(lib().tsb_contract2_bits(ctx(), _ptr(lhs), len(lhs_wires), _i32(lhs_wires), _ptr(rhs), len(rhs_wires),
+                                    _i32(rhs_wires), _ptr(out), len(out_wires), _i32(out_wires), int(n_wires),
+                                    _i32([2] * int(n_wires)), stream()))
 
 
 def all_ones(t: Any, mode: int) -> bool:

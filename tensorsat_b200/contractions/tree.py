@@ -46,6 +46,7 @@ class TreeContraction(Contraction):
         wire_is_free: Sequence[bool] | None = None,
         batch_log2: int = -1,
         force_generic: bool = False,
+        bit_packing: bool = True,
     ) -> None:
         super().__init__(box_class, wiring)
         if not issubclass(box_class, _CudaTensorBox):
@@ -82,7 +83,7 @@ class TreeContraction(Contraction):
         self._tree = tree
         self._wire_is_free = None if wire_is_free is None else [bool(x) for x in wire_is_free]
         self._batch_log2 = int(batch_log2)
-        self._flags = _native.PLAN_FORCE_GENERIC if force_generic else 0
+        self._flags = (_native.PLAN_FORCE_GENERIC if force_generic else 0) | (0 if bit_packing else _native.PLAN_NO_PACK)
         self._plan: _native.Plan | None = None
 
     @property

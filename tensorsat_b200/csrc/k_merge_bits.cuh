@@ -1,0 +1,227 @@
+// k_merge_bits.cuh — the boolean-semiring monotone merge on BIT-PACKED relations (1 bit per entry).
+//
+// SURVEY.md §8(f) N4 / the reference authors' planned "Binary Packing" (paper/typst/main.typ:336-339):
+// the steps of FinRel._contract2 (tensorsat/lang/fin_rel.py:255-288) that dominate a SAT plan are
+// bandwidth-bound, and a 0/1 relation stored one bit per entry moves 8x fewer bytes.  Entry i of a
+// packed tensor is bit (i & 31) of 32-bit word (i >> 5); tensors smaller than a word are padded.
+//
+// Same scheme as k_merge_sat (one global wire order => operand address bits are an order-preserving
+// subsequence of the output's), one thread per 16-byte output vector = 128 entries = the 7 lowest
+// output address bits.  Per operand and summed-wire combination the thread needs the aligned chunk of
+// 2^c bits (c = number of those 7 bits the operand depends on) that the vector touches: ONE load of
+// 4 / 8 / 16 bytes, then an expansion to 128 lanes.  Word-level lanes (bits 5, 6) are register moves;
+// in-word lanes (bits 0..4) go through a 256-entry shared-memory table per operand built once per CTA
+// (two tables when the operand has 4 of the 5 in-word bits), so any of the 128 x 128 lane-mask pairs
+// runs on the same code.  Combine: 4 LOP3 per summed-wire combination; one 16-byte store.
+// Bound: HBM at 1/8 byte per entry (algorithmic bytes = (|lhs| + |rhs| + |out|) / 8).
+#pragma once
+#include "k_merge.cuh"
+
+namespace tsb {
+
+constexpr int kBitsThreads = 256;
+constexpr int kBitsG = 2;        // output vectors per thread in flight
+constexpr int kBitsVecBits = 7;  // entries per 16-byte vector, log2
+
+TSB_HD int pext_bits(int e, int mask, int nbits) {
+  int r = 0, o = 0;
+  for (int b = 0; b < nbits; b++)
+    if (mask >> b & 1) { r |= ((e >> b) & 1) << o; o++; }
+  return r;
+}
+
+struct BitsLane {  // uniform per launch and operand
+  int c;    // lanes bits the operand depends on (0..7)
+  int c5;   // of which in-word (bits 0..4)
+  int hi2;  // mask of word-level bits (output bits 5, 6)
+};
+
+TSB_HD BitsLane bits_lane(int nib7) {
+  BitsLane l;
+  int c = 0, c5 = 0;
+  for (int b = 0; b < 7; b++)
+    if (nib7 >> b & 1) { c++; if (b < 5) c5++; }
+  l.c = c; l.c5 = c5; l.hi2 = nib7 >> 5;
+  return l;
+}
+
+// lut[t * 256 + b]: the 32 in-word lanes produced by byte t of a sub-chunk whose value is b
+TSB_D void bits_build_lut(int nib7, uint32_t* lut) {
+  const int lo5 = nib7 & 31;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const uint32_t v = (uint32_t)(i & 255) << (8 * (i >> 8));
+    uint32_t x = 0;
+    for (int e = 0; e < 32; e++) x |= ((v >> pext_bits(e, lo5, 5)) & 1u) << e;
+    lut[i] = x;
+  }
+}
+
+// X[w] = the 32 lanes of output word w: lane e of word w reads chunk bit pext(w*32+e, nib7)
+TSB_D void bits_fetch(const uint32_t* __restrict__ base, uint64_t a, const BitsLane ln, const uint32_t* lut,
+                      uint32_t X[4]) {
+  const uint32_t* p = base + (a >> 5);
+  uint32_t e0, e1 = 0, e2 = 0, e3 = 0;
+  if (ln.c5 == 5) {
+    if (ln.hi2 == 0) { e0 = *p; }
+    else if (ln.hi2 == 3) { const uint4 t = *(const uint4*)p; e0 = t.x; e1 = t.y; e2 = t.z; e3 = t.w; }
+    else { const uint2 t = *(const uint2*)p; e0 = t.x; e1 = t.y; }
+  } else {
+    // sub-word sub-chunks: the chunk (<= 64 bits) starts at bit (a & 31) of *p and never straddles
+    uint64_t v;
+    if (ln.c == 6) { const uint2 t = *(const uint2*)p; v = (uint64_t)t.x | ((uint64_t)t.y << 32); }
+    else v = (uint64_t)(*p >> (uint32_t)(a & 31));
+    const uint32_t mask = (1u << (1 << ln.c5)) - 1u;
+    const int nsub = ln.hi2 == 0 ? 1 : ln.hi2 == 3 ? 4 : 2;
+    uint32_t s0 = (uint32_t)v & mask, s1 = (uint32_t)(v >> (1 << ln.c5)) & mask,
+             s2 = (uint32_t)(v >> (2 << ln.c5)) & mask, s3 = (uint32_t)(v >> (3 << ln.c5)) & mask;
+    if (ln.c5 == 4) {
+      e0 = lut[s0 & 255] | lut[256 + (s0 >> 8)];
+      if (nsub > 1) e1 = lut[s1 & 255] | lut[256 + (s1 >> 8)];
+      if (nsub > 2) { e2 = lut[s2 & 255] | lut[256 + (s2 >> 8)]; e3 = lut[s3 & 255] | lut[256 + (s3 >> 8)]; }
+    } else {
+      e0 = lut[s0];
+      if (nsub > 1) e1 = lut[s1];
+      if (nsub > 2) { e2 = lut[s2]; e3 = lut[s3]; }
+    }
+  }
+  switch (ln.hi2) {
+    case 0: X[0] = X[1] = X[2] = X[3] = e0; break;
+    case 1: X[0] = e0; X[1] = e1; X[2] = e0; X[3] = e1; break;
+    case 2: X[0] = X[1] = e0; X[2] = X[3] = e1; break;
+    default: X[0] = e0; X[1] = e1; X[2] = e2; X[3] = e3; break;
+  }
+}
+
+// d.nibL / d.nibR hold 7-bit lane masks, d.n_vec = 2^(R-7), all operand offsets are in entries (= bits).
+// bitoffL / bitoffR: where the operand (a slice of a shared tensor) starts inside lhs / rhs.
+__global__ void __launch_bounds__(kBitsThreads, 4)
+k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ lhs, uint64_t bitoffL,
+             const uint32_t* __restrict__ rhs, uint64_t bitoffR, uint4* __restrict__ out) {
+  __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
+  __shared__ int64_t kL[256], kR[256];
+  __shared__ uint32_t lutL[512], lutR[512];
+  __shared__ RunsSmem runsL, runsR;
+  const int nt = 1 << d.tile_bits;
+  for (int i = threadIdx.x; i < nt; i += kBitsThreads) {
+    tabL[i] = (uint32_t)deposit(d.loL, (uint64_t)i);
+    tabR[i] = (uint32_t)deposit(d.loR, (uint64_t)i);
+  }
+  for (int i = threadIdx.x; i < (1 << d.kbits); i += kBitsThreads) {
+    int64_t a = 0, b = 0;
+    for (int q = 0; q < d.kbits; q++)
+      if (i >> q & 1) { a += d.ksL[q]; b += d.ksR[q]; }
+    kL[i] = a;
+    kR[i] = b;
+  }
+  bits_build_lut(d.nibL, lutL);
+  bits_build_lut(d.nibR, lutR);
+  runs_to_smem(d.hiL, runsL);
+  runs_to_smem(d.hiR, runsR);
+  __syncthreads();
+  const BitsLane lnL = bits_lane(d.nibL), lnR = bits_lane(d.nibR);
+  const int K = 1 << d.kbits;
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const bool acc_out = d.accumulate != 0, has_rhs = d.has_rhs != 0;
+  int64_t tile = blockIdx.x;
+  uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
+  uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
+  while (tile < n_tiles) {
+    const uint64_t baseL = bitoffL + offL, baseR = bitoffR + offR;
+    uint4* outp = out + (tile << d.tile_bits);
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {
+      offL = deposit_warp(runsL, (uint64_t)next);
+      offR = deposit_warp(runsR, (uint64_t)next);
+    }
+    for (int v0 = threadIdx.x; v0 < nt; v0 += kBitsThreads * kBitsG) {
+      uint64_t aL[kBitsG], aR[kBitsG];
+      bool on[kBitsG];
+      uint32_t acc[kBitsG][4];
+#pragma unroll
+      for (int g = 0; g < kBitsG; g++) {
+        const int vi = v0 + g * kBitsThreads;
+        on[g] = vi < nt;
+        aL[g] = baseL + tabL[on[g] ? vi : 0];
+        aR[g] = baseR + tabR[on[g] ? vi : 0];
+        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0;
+      }
+      if (acc_out) {
+#pragma unroll
+        for (int g = 0; g < kBitsG; g++)
+          if (on[g]) {
+            const uint4 p = outp[v0 + g * kBitsThreads];
+            acc[g][0] = p.x; acc[g][1] = p.y; acc[g][2] = p.z; acc[g][3] = p.w;
+          }
+      }
+      for (int kk = 0; kk < K; kk++) {
+        const uint64_t sl = (uint64_t)kL[kk], sr = (uint64_t)kR[kk];
+        uint32_t XL[kBitsG][4], XR[kBitsG][4];
+#pragma unroll
+        for (int g = 0; g < kBitsG; g++) {
+          if (on[g]) {
+            bits_fetch(lhs, aL[g] + sl, lnL, lutL, XL[g]);
+            if (has_rhs) bits_fetch(rhs, aR[g] + sr, lnR, lutR, XR[g]);
+            else XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0xffffffffu;
+          } else {
+            XL[g][0] = XL[g][1] = XL[g][2] = XL[g][3] = 0;
+            XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kBitsG; g++) {
+          acc[g][0] |= XL[g][0] & XR[g][0]; acc[g][1] |= XL[g][1] & XR[g][1];
+          acc[g][2] |= XL[g][2] & XR[g][2]; acc[g][3] |= XL[g][3] & XR[g][3];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kBitsG; g++)
+        if (on[g]) outp[v0 + g * kBitsThreads] = make_uint4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+    }
+    tile = next;
+  }
+}
+
+// ---- conversions between the byte (0/1 per uint8) and the bit-packed representation -----------------
+
+// four 0/1 bytes -> 4 bits (byte j -> bit j): the partial products land on distinct bits, no carries
+TSB_D uint32_t pack4(uint32_t w) { return ((w * 0x01020408u) >> 24) & 0xfu; }
+// 4 bits -> four 0/1 bytes
+TSB_D uint32_t unpack4(uint32_t n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; }
+
+static __global__ void k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n_entries) {
+  const int64_t n_words = (n_entries + 31) >> 5;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = w << 5;
+    uint32_t bits = 0;
+    if (e0 + 32 <= n_entries) {
+      const uint4 a = *(const uint4*)(src + e0), b = *(const uint4*)(src + e0 + 16);
+      bits = pack4(a.x) | pack4(a.y) << 4 | pack4(a.z) << 8 | pack4(a.w) << 12 | pack4(b.x) << 16 | pack4(b.y) << 20 |
+             pack4(b.z) << 24 | pack4(b.w) << 28;
+    } else {
+      for (int64_t j = e0; j < n_entries; j++) bits |= (uint32_t)(src[j] != 0) << (j - e0);
+    }
+    dst[w] = bits;
+  }
+}
+
+static __global__ void k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n_entries,
+                                     int accumulate) {
+  const int64_t n_vec = (n_entries + 15) >> 4;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = (src[v >> 1] >> ((v & 1) * 16)) & 0xffffu;
+    const int64_t e0 = v << 4;
+    if (e0 + 16 <= n_entries) {
+      uint4 r = make_uint4(unpack4(h), unpack4(h >> 4), unpack4(h >> 8), unpack4(h >> 12));
+      uint4* q = (uint4*)(dst + e0);
+      if (accumulate) { const uint4 p = *q; r.x |= p.x; r.y |= p.y; r.z |= p.z; r.w |= p.w; }
+      *q = r;
+    } else {
+      for (int64_t j = e0; j < n_entries; j++) {
+        const uint8_t b = (uint8_t)((h >> (j - e0)) & 1u);
+        dst[j] = accumulate ? (uint8_t)(dst[j] | b) : b;
+      }
+    }
+  }
+}
+
+}  // namespace tsb

@@ -396,11 +396,13 @@ struct MergeArgs {
 
 // lhs_bits / rhs_bits / out_bits: bit labels MSB first.  Labels of lhs/rhs not in out are summed.
 // Returns ok=false if the monotone-merge preconditions do not hold.
+// vbits: output address bits covered by one thread's vector (4 = 16 bytes of uint8 entries, 7 = 16 bytes of
+// bit-packed entries); nibL / nibR are vbits-wide lane masks.
 inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs_bits, const BitLabels& out_bits,
-                                 bool accumulate) {
+                                 bool accumulate, int vbits = 4) {
   MergeArgs m;
   const int R = (int)out_bits.size();
-  if (R < 4 || R > 62) return m;
+  if (R < vbits || R > 62) return m;
   if (has_dups(lhs_bits) || has_dups(out_bits) || (rhs_bits && has_dups(*rhs_bits))) return m;
   auto lp = positions(lhs_bits);
   std::map<int64_t, int> rp;
@@ -419,7 +421,7 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
       if (it == pp.end()) continue;
       if (it->second <= last) return false;
       last = it->second;
-      if (j < 4) {
+      if (j < vbits) {
         if (it->second != nlow) return false;  // must be the operand's lowest address bits
         nib |= 1 << j;
         nlow++;
@@ -436,13 +438,13 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
   d.nibL = nibL; d.nibR = nibR;
   d.has_rhs = rhs_bits ? 1 : 0;
   d.accumulate = accumulate ? 1 : 0;
-  const int vb = R - 4;
-  d.tile_bits = std::min(vb, std::min(kMergeTileBits, std::max(7, R - 14)));
+  const int vb = R - vbits;
+  d.tile_bits = std::min(vb, std::min(kMergeTileBits, std::max(vbits == 4 ? 7 : 8, vb - 10)));
   d.n_vec = int64_t(1) << vb;
-  for (int j = 4; j < R; j++) {
+  for (int j = vbits; j < R; j++) {
     const int64_t lab = out_bits[R - 1 - j];
-    const bool lo = (j - 4) < d.tile_bits;
-    const int in = lo ? j - 4 : j - 4 - d.tile_bits;
+    const bool lo = (j - vbits) < d.tile_bits;
+    const int in = lo ? j - vbits : j - vbits - d.tile_bits;
     auto il = lp.find(lab);
     if (il != lp.end()) runs_add(lo ? d.loL : d.hiL, in, il->second);
     auto ir = rp.find(lab);
@@ -511,6 +513,14 @@ template <> void launch_merge_cnt_t<uint8_t, uint8_t>(tsb_ctx*, const MergeDesc&
 template <> void launch_merge_cnt_t<uint8_t, int32_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
 template <> void launch_merge_cnt_t<int32_t, uint8_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
 template <> void launch_merge_cnt_t<int32_t, int32_t>(tsb_ctx*, const MergeDesc&, const void*, const void*, void*, cudaStream_t);
+
+// bit-packed boolean relations (k_merge_bits.cuh); d from make_merge_desc(..., vbits = 7)
+void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bitoff_l, const void* r,
+                       uint64_t bitoff_r, void* o, cudaStream_t s);
+void launch_pack_bits(tsb_ctx* ctx, const void* src_u8, void* dst_bits, int64_t n_entries, cudaStream_t s);
+void launch_unpack_bits(tsb_ctx* ctx, const void* src_bits, void* dst_u8, int64_t n_entries, bool accumulate,
+                        cudaStream_t s);
+inline size_t packed_bytes(int64_t n_entries) { return (size_t)std::max<int64_t>(16, (n_entries + 7) / 8); }
 
 bool merge_wide_supported(const MergeDesc& d, const void* l, int dl, const void* r, int dr, const void* o);
 void launch_merge_wide(tsb_ctx* ctx, const MergeDesc& d, const void* l, int dl, const void* r, int dr, void* o,

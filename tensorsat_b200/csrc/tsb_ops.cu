@@ -598,6 +598,50 @@ int tsb_convert(tsb_ctx* ctx, const void* src, int src_dtype, void* dst, int dst
   TSB_API_END
 }
 
+int tsb_pack_bits(tsb_ctx* ctx, const void* src_u8, void* dst_bits, int64_t n, tsb_stream stream) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  TSB_CHECK(src_u8 && dst_bits && n >= 1, TSB_ERR_INVALID, "pack_bits: null buffer or empty tensor");
+  TSB_CHECK(((uintptr_t)src_u8 & 15) == 0 && ((uintptr_t)dst_bits & 15) == 0, TSB_ERR_INVALID,
+            "pack_bits: buffers must be 16-byte aligned");
+  launch_pack_bits(ctx, src_u8, dst_bits, n, (cudaStream_t)stream);
+  TSB_API_END
+}
+
+int tsb_unpack_bits(tsb_ctx* ctx, const void* src_bits, void* dst_u8, int64_t n, int accumulate, tsb_stream stream) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  TSB_CHECK(src_bits && dst_u8 && n >= 1, TSB_ERR_INVALID, "unpack_bits: null buffer or empty tensor");
+  TSB_CHECK(((uintptr_t)src_bits & 15) == 0 && ((uintptr_t)dst_u8 & 15) == 0, TSB_ERR_INVALID,
+            "unpack_bits: buffers must be 16-byte aligned");
+  launch_unpack_bits(ctx, src_bits, dst_u8, n, accumulate != 0, (cudaStream_t)stream);
+  TSB_API_END
+}
+
+int tsb_contract2_bits(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* lhs_wires, const void* rhs,
+                       int rhs_rank, const int32_t* rhs_wires, void* out, int out_rank, const int32_t* out_wires,
+                       int n_wires, const int32_t* wire_extents, tsb_stream stream) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  TSB_CHECK(lhs && rhs && out && lhs_wires && rhs_wires && out_wires && wire_extents, TSB_ERR_INVALID, "null argument");
+  auto chk = [&](const int32_t* ws, int r) {
+    TSB_CHECK(r >= 0 && r <= TSB_MAX_RANK, TSB_ERR_INVALID, "rank out of range");
+    for (int i = 0; i < r; i++) {
+      TSB_CHECK(ws[i] >= 0 && ws[i] < n_wires, TSB_ERR_INVALID, "wire %d out of range", ws[i]);
+      TSB_CHECK(wire_extents[ws[i]] == 2, TSB_ERR_UNSUPPORTED, "bit-packed contraction needs extent 2 on every wire");
+    }
+  };
+  chk(lhs_wires, lhs_rank); chk(rhs_wires, rhs_rank); chk(out_wires, out_rank);
+  BitLabels lb = bit_labels(lhs_wires, lhs_rank, wire_extents);
+  BitLabels rb = bit_labels(rhs_wires, rhs_rank, wire_extents);
+  BitLabels ob = bit_labels(out_wires, out_rank, wire_extents);
+  MergeArgs m = make_merge_desc(lb, &rb, ob, false, 7);
+  TSB_CHECK(m.ok && m.d.kbits <= 8, TSB_ERR_UNSUPPORTED,
+            "bit-packed contraction needs one wire order for all three tensors, out_rank >= 7 and <= 8 summed wires");
+  launch_merge_bits(ctx, m.d, lhs, 0, rhs, 0, out, (cudaStream_t)stream);
+  TSB_API_END
+}
+
 int tsb_all_ones(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result, tsb_stream stream) {
   TSB_API_BEGIN
   check_ctx(ctx);

@@ -51,6 +51,8 @@ struct PNode {
   bool is_out = false;           // the root, written straight into the caller's buffer
   bool post = false;             // shared node computed AFTER the slice loop (tail of the tree)
   bool gathered = false;         // per-slice node stored with the sliced wires leading: slice s fills block s
+  bool packed = false;           // boolean relation stored one bit per entry (k_merge_bits.cuh)
+  int64_t stored_numel() const { return reg_numel * ((shared || gathered) ? s_numel : 1); }
   std::vector<int32_t> stored() const {  // axis order of the stored buffer
     std::vector<int32_t> v;
     if (shared || gathered) v = slab;
@@ -59,7 +61,7 @@ struct PNode {
   }
 };
 
-enum OpKind { OP_LEAF = 0, OP_STEP = 1, OP_FINAL_PERMUTE = 2 };
+enum OpKind { OP_LEAF = 0, OP_STEP = 1, OP_FINAL_PERMUTE = 2, OP_PACK = 3, OP_UNPACK = 4 };
 
 struct POp {
   int kind = OP_STEP;
@@ -67,6 +69,8 @@ struct POp {
   int lhs = -1, rhs = -1, out = -1;  // node ids
   bool use_merge = false;
   bool use_gemm = false;  // lowered at run time: transposes + tcgen05 int8 GEMM
+  bool use_bits = false;  // both operands and the result are bit-packed: k_merge_bits
+  double alg_bytes_u8 = 0;  // algorithmic bytes at one byte per boolean entry
   MergeDesc md{};
   // generic description (wires + extents) used when the merge kernel does not apply
   std::vector<int32_t> lw, rw, ow;
@@ -417,6 +421,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     const double nl = (double)prod_ext(op.lw, P.wext), nr = (double)prod_ext(op.rw, P.wext),
                  no = (double)prod_ext(op.ow, P.wext);
     op.alg_bytes = nl * esz(op.lhs) + nr * esz(op.rhs) + no * esz(op.out);
+    op.alg_bytes_u8 = op.alg_bytes;
     op.alg_ops = 2.0 * std::exp2(lb + lm + ln + lk);
     P.ops.push_back(op);
   }
@@ -487,6 +492,86 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     }
   }
 
+  // ---- bit-packed representation for the boolean semiring -----------------------------
+  // A step that touches a tensor of >= 2^kPackMinLog2 entries runs on bit-packed operands (k_merge_bits):
+  // 8x fewer bytes on the steps that are HBM-bound.  Conversions (k_pack_bits / k_unpack_bits) are
+  // inserted where a tensor crosses between the two representations; by construction they fall on small
+  // tensors (the leaves' side of the tree and the gathered tail), except around GEMM-lowered steps.
+  if (P.mode == TSB_SAT && !force_generic && !(P.flags & TSB_PLAN_NO_PACK)) {
+    // test knob: TSB_PACK_MIN_LOG2 lowers the threshold so that small parity cases take the packed path
+    const char* env_min = std::getenv("TSB_PACK_MIN_LOG2");
+    const double kPackMinLog2 = env_min ? std::atof(env_min) : 20.0;
+    const int NN0 = (int)P.nodes.size();
+    for (auto& op : P.ops) {
+      if (op.kind != OP_STEP || !op.use_merge) continue;
+      if (P.stack_out && op.out == P.root) continue;
+      const double big = std::max({(double)prod_ext(op.lw, P.wext), (double)prod_ext(op.rw, P.wext),
+                                   (double)prod_ext(op.ow, P.wext)});
+      if (std::log2(big) < kPackMinLog2) continue;
+      BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
+      BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
+      BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
+      MergeArgs m = make_merge_desc(lb, &rb, ob, false, 7);
+      if (!m.ok || m.d.kbits > 8) continue;
+      op.use_bits = true;
+      op.md = m.d;
+    }
+    std::vector<char> made_packed(NN0, 0), needs_packed(NN0, 0), needs_bytes(NN0, 0);
+    for (auto& op : P.ops) {
+      if (op.use_bits) {
+        made_packed[op.out] = 1;
+        needs_packed[op.lhs] = needs_packed[op.rhs] = 1;
+      } else {
+        if (op.lhs >= 0) needs_bytes[op.lhs] = 1;
+        if (op.rhs >= 0) needs_bytes[op.rhs] = 1;
+      }
+    }
+    for (int i = 0; i < NN0; i++) {
+      const PNode& nd = P.nodes[i];
+      if (nd.is_out || nd.gathered || i == P.root) needs_bytes[i] = 1;
+    }
+    std::vector<int> twin(NN0, -1);  // id of the packed version when the node itself stays in bytes
+    std::vector<POp> ops2;
+    ops2.reserve(P.ops.size() + 64);
+    auto packed_id = [&](int i) { return P.nodes[i].packed ? i : twin[i]; };
+    for (int i = 0; i < NN0; i++) {
+      if (made_packed[i] && !needs_bytes[i]) { P.nodes[i].packed = true; continue; }
+      if (!(made_packed[i] ? true : needs_packed[i])) continue;
+      // a second node holding the packed version
+      PNode t = P.nodes[i];
+      t.packed = true;
+      t.is_out = false;
+      t.offset = -1;
+      if (!made_packed[i] && t.gathered) { t.gathered = false; t.shared = true; t.post = true; }  // packed after the loop
+      if (made_packed[i]) t.gathered = false;  // plain per-slice temporary, unpacked into the gathered block
+      twin[i] = (int)P.nodes.size();
+      P.nodes.push_back(t);
+    }
+    for (auto& op0 : P.ops) {
+      POp op = op0;
+      const int y = op.out;
+      if (op.use_bits) {
+        op.lhs = packed_id(op.lhs);
+        op.rhs = packed_id(op.rhs);
+        op.out = packed_id(y);
+        op.alg_bytes = op.alg_bytes_u8 / 8.0;
+      }
+      ops2.push_back(op);
+      if (twin[y] < 0) continue;
+      POp cv;
+      cv.kind = made_packed[y] ? OP_UNPACK : OP_PACK;
+      cv.lhs = made_packed[y] ? twin[y] : y;
+      cv.out = made_packed[y] ? y : twin[y];
+      cv.per_slice = !P.nodes[cv.out].shared;
+      cv.alg_bytes = 0;  // representation change, not algorithmic work
+      ops2.push_back(cv);
+      P.info.n_conversions++;
+    }
+    P.ops.swap(ops2);
+    for (auto& op : P.ops) if (op.use_bits) P.info.n_packed_steps++;
+  }
+  const int NN = (int)P.nodes.size();  // tree nodes + packed twins (the stacked result buffer comes later)
+
   // ---- schedule of the once-only parts: waves of mutually independent ops ---------------------------
   // pre = before the slice loop, post = after it (tail of the tree on gathered slices)
   std::vector<int> producer(P.nodes.size() + 1, -1);
@@ -518,7 +603,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   // loop, gathered results) is allocated outside the loop's reusable region.
   for (int i = 0; i < (int)P.nodes.size(); i++) {
     PNode& nd = P.nodes[i];
-    nd.bytes = (size_t)(nd.reg_numel * ((nd.shared || nd.gathered) ? nd.s_numel : 1) * dtype_size(nd.dtype));
+    nd.bytes = nd.packed ? packed_bytes(nd.stored_numel()) : (size_t)(nd.stored_numel() * dtype_size(nd.dtype));
   }
   const int n_pre = pre_ops.empty() ? 0 : P.ops[pre_ops.back()].wave + 1;
   const int n_loop = (int)P.slice_ops.size();
@@ -558,7 +643,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     for (int i = 0; i < (int)P.ops.size(); i++) at[tpos[i]].push_back(i);
     for (int t = 0; t < T_END; t++) {
       if (t == n_pre) {
-        for (int i = 0; i < 2 * L - 1; i++)
+        for (int i = 0; i < NN; i++)
           if (P.nodes[i].gathered) {
             P.nodes[i].offset = fl.alloc((int64_t)P.nodes[i].bytes);
             P.gathered_nodes.push_back(i);
@@ -577,7 +662,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
           }
       if (t == n_pre + n_loop - 1) {
         // end of the loop: shared operands whose last consumer was inside the loop, at an earlier position
-        for (int nd = 0; nd < 2 * L - 1; nd++)
+        for (int nd = 0; nd < NN; nd++)
           if (P.nodes[nd].shared && P.nodes[nd].offset >= 0 && last_use[nd] == t && !freed.count(nd)) {
             bool used_here = false;
             for (int i : at[t]) used_here = used_here || P.ops[i].lhs == nd || P.ops[i].rhs == nd;
@@ -654,9 +739,11 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     if (op.per_slice) {
       P.info.n_kernels_per_slice++;
       P.info.alg_bytes_per_slice += op.alg_bytes;
+      P.info.alg_bytes_u8_per_slice += op.alg_bytes_u8;
       P.info.alg_ops_per_slice += op.alg_ops;
     } else {
       P.info.alg_bytes_shared += op.alg_bytes;
+      P.info.alg_bytes_u8_shared += op.alg_bytes_u8;
       P.info.alg_ops_shared += op.alg_ops;
     }
     if (op.kind == OP_STEP) mx = std::max(mx, ilog2(std::max<int64_t>(1, prod_ext(op.ow, P.wext))));
@@ -688,9 +775,31 @@ int64_t shared_offset(const tsb_plan& P, const PNode& nd, const std::vector<int6
 void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vector<int64_t>* digits, bool accumulate,
               cudaStream_t stream) {
   tsb_ctx* ctx = P.ctx;
+  if (op.kind == OP_PACK || op.kind == OP_UNPACK) {
+    const PNode& src = P.nodes[op.lhs];
+    const PNode& dst = P.nodes[op.out];
+    if (op.kind == OP_PACK) {
+      launch_pack_bits(ctx, base + src.offset, base + dst.offset, src.stored_numel(), stream);
+      return;
+    }
+    void* pd = dst.is_out ? out_ptr : (void*)(base + dst.offset);
+    if (op.per_slice && dst.gathered) pd = (uint8_t*)pd + shared_offset(P, dst, *digits);
+    launch_unpack_bits(ctx, base + src.offset, pd, src.stored_numel(), accumulate && dst.is_out, stream);
+    return;
+  }
   const PNode& a = P.nodes[op.lhs];
   const PNode& b = P.nodes[op.rhs];
   const PNode& o = P.nodes[op.out];
+  if (op.use_bits) {
+    // packed operands: a slice of a shared tensor is addressed by its bit offset
+    uint64_t bl = 0, br = 0;
+    if (op.per_slice) {
+      if (a.shared) bl = (uint64_t)shared_offset(P, a, *digits);
+      if (b.shared) br = (uint64_t)shared_offset(P, b, *digits);
+    }
+    launch_merge_bits(ctx, op.md, base + a.offset, bl, base + b.offset, br, base + o.offset, stream);
+    return;
+  }
   const uint8_t* pl = base + a.offset;
   const uint8_t* pr = base + b.offset;
   if (op.per_slice) {
@@ -777,7 +886,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     if (!first) os << ",";
     first = false;
     const PNode& o = plan->nodes[op.out];
-    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_STEP ? (op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
+    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
        << ",\"small\":" << (op.small ? 1 : 0) << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR

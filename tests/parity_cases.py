@@ -219,6 +219,115 @@ def test_counting_merge_int64_kernel(tl, tr):
         assert np.array_equal(Od.cpu().numpy().reshape((2,) * R), want)
 
 
+def _pack_host(t):
+    return np.packbits(t.reshape(-1).astype(np.uint8), bitorder="little")
+
+
+@pytest.mark.parametrize("n", [1, 5, 16, 31, 32, 33, 100, 4096, 70001])
+def test_pack_unpack_bits_round_trip(n):
+    """Byte <-> bit conversions against numpy.packbits (little-endian bit order inside each 32-bit word)."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(n)
+    t = (rng.random(n) < 0.4).astype(np.uint8)
+    dev = _native.device()
+    src = torch.from_numpy(t).to(dev)
+    packed = torch.zeros(_native.packed_nbytes(n), dtype=torch.uint8, device=dev)
+    _native.pack_bits(src, packed)
+    want = _pack_host(t)
+    assert np.array_equal(packed.cpu().numpy()[: len(want)], want)
+    back = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+    _native.unpack_bits(packed, back)
+    assert np.array_equal(back.cpu().numpy(), t)
+    other = (rng.random(n) < 0.3).astype(np.uint8)
+    acc = torch.from_numpy(other).to(dev)
+    _native.unpack_bits(packed, acc, accumulate=True)
+    assert np.array_equal(acc.cpu().numpy(), t | other)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_contract2_bits_random_lane_masks(seed):
+    """k_merge_bits through tsb_contract2_bits: random subsets of the output wires on each operand (every
+    in-word / word-level lane pattern class), 0..3 summed wires, against the oracle's boolean einsum."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(100 + seed)
+    dev = _native.device()
+    for trial in range(6):
+        R = int(rng.integers(7, SCALE["big_bits"] - 2))
+        nk = int(rng.integers(0, 4))
+        ks = list(range(nk))
+        out_w = list(range(nk, R + nk))
+        # how many of the 7 lowest output wires each operand holds decides the code path: force variety
+        low = out_w[-7:]
+        pick_l = [w for w in low if rng.random() < (0.15, 0.5, 0.85, 1.0)[trial % 4]]
+        pick_r = [w for w in low if rng.random() < (1.0, 0.85, 0.3, 0.6)[trial % 4]]
+        hi = out_w[:-7]
+        lw = ks + sorted(set(pick_l) | set(int(w) for w in hi if rng.random() < 0.5))
+        rw_k = [k for k in ks if rng.random() < 0.7]
+        rw = rw_k + sorted((set(out_w) - set(lw)) | set(pick_r) | set(int(w) for w in hi if rng.random() < 0.4))
+        L = (rng.random((2,) * len(lw)) < 0.35).astype(np.uint8)
+        Rr = (rng.random((2,) * len(rw)) < 0.45).astype(np.uint8)
+        bufs = []
+        for t in (L, Rr):
+            b = torch.zeros(_native.packed_nbytes(t.size), dtype=torch.uint8, device=dev)
+            _native.pack_bits(torch.from_numpy(t.reshape(-1)).to(dev), b)
+            bufs.append(b)
+        ob = torch.zeros(_native.packed_nbytes(1 << R), dtype=torch.uint8, device=dev)
+        _native.contract2_bits(bufs[0], lw, bufs[1], rw, ob, out_w, R + nk)
+        want = O.contract2(L, lw, Rr, rw, out_w, mode="sat")
+        got = np.unpackbits(ob.cpu().numpy(), bitorder="little")[: 1 << R].reshape((2,) * R)
+        assert np.array_equal(got, want), (R, nk, lw, rw)
+
+
+def test_contract2_bits_every_lane_class():
+    """All 128 lane masks on one operand (the other holds every wire), on either side."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(77)
+    dev = _native.device()
+    R = 9
+    out_w = list(range(1, R + 1))          # wire 0 is summed
+    full = [0] + out_w
+    F = (rng.random((2,) * len(full)) < 0.5).astype(np.uint8)
+    fb = torch.zeros(_native.packed_nbytes(F.size), dtype=torch.uint8, device=dev)
+    _native.pack_bits(torch.from_numpy(F.reshape(-1)).to(dev), fb)
+    for mask in range(128):
+        low = [out_w[R - 1 - j] for j in range(6, -1, -1) if mask >> j & 1]   # output bit j = wire out_w[R-1-j]
+        sw = [0, out_w[0]] + low
+        S = (rng.random((2,) * len(sw)) < 0.5).astype(np.uint8)
+        sb = torch.zeros(_native.packed_nbytes(S.size), dtype=torch.uint8, device=dev)
+        _native.pack_bits(torch.from_numpy(S.reshape(-1)).to(dev), sb)
+        for small_first in (True, False):
+            ob = torch.zeros(_native.packed_nbytes(1 << R), dtype=torch.uint8, device=dev)
+            if small_first:
+                _native.contract2_bits(sb, sw, fb, full, ob, out_w, R + 1)
+            else:
+                _native.contract2_bits(fb, full, sb, sw, ob, out_w, R + 1)
+            want = O.contract2(S, sw, F, full, out_w, mode="sat")
+            got = np.unpackbits(ob.cpu().numpy(), bitorder="little")[: 1 << R].reshape((2,) * R)
+            assert np.array_equal(got, want), (mask, small_first)
+
+
+def test_contract2_bits_rejects_what_it_cannot_do():
+    import torch
+
+    from tensorsat_b200 import _native
+
+    dev = _native.device()
+    b = torch.zeros(64, dtype=torch.uint8, device=dev)
+    with pytest.raises(NotImplementedError):   # out_rank < 7
+        _native.contract2_bits(b, [0, 1], b, [1, 2], b, [0, 2], 3)
+    with pytest.raises(NotImplementedError):   # wire order of the output disagrees with the operands
+        _native.contract2_bits(b, list(range(8)), b, list(range(8)), b, list(range(7, -1, -1)), 8)
+
+
 @pytest.mark.parametrize("k,r", [(9, 0), (13, 0), (14, 2), (12, 5), (17, 1)])
 def test_contract2_many_summed_wires(k, r):
     """Dot-product-like steps (many summed wires, few outputs) are split over the summed wires (split-K)."""
@@ -303,6 +412,40 @@ def _oracle_tree(flat, tree, mode="sat"):
     leaves = [b.tensor for b in flat.boxes]
     return O.execute_tree(tree.network.inputs, tree.network.output, leaves, tree.ssa_path,
                           tree.sliced_wires, mode=mode, size_dict=tree.network.size_dict)
+
+
+@pytest.mark.parametrize("k,n,m,seed,target,batch", [(3, 14, 50, 0, 10, 6), (3, 15, 55, 1, 11, 9), (4, 14, 110, 2, 30, 24),
+                                                    (3, 16, 62, 3, 12, 24), (3, 15, 58, 4, 9, 3)])
+def test_bit_packed_plans_give_the_same_solution_tensors(monkeypatch, k, n, m, seed, target, batch):
+    """All-solutions tensors (2^n entries, zeros and ones) through plans whose large steps run bit-packed
+    (threshold lowered by the test knob so that these sizes qualify): pre / per-slice / gathered / post paths,
+    conversions on both sides, against brute force and against the same plan without packing."""
+    monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    cnf = CNFInstance.random(k, n, m, rng=seed)
+    flat, net = _network_and_leaves(cnf.diagram())
+    tree = find_tree_elimination(net, trials=2, seed=seed)
+    if target < 30:   # output wires cannot be sliced: slice a few internal wires instead
+        internal = [w for w in range(n, net.num_wires)]
+        rs = np.random.default_rng(seed)
+        tree = tree.with_sliced(sorted(int(w) for w in rs.choice(internal, size=2 + seed % 2, replace=False)))
+    want = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    assert 0 < np.count_nonzero(want) < want.size
+    packed = TreeContraction(CudaFinRel, flat.wiring, tree=tree, batch_log2=batch)
+    plain = TreeContraction(CudaFinRel, flat.wiring, tree=tree, batch_log2=batch, bit_packing=False)
+    assert packed.plan().info["n_packed_steps"] > 0 and plain.plan().info["n_packed_steps"] == 0
+    assert np.array_equal(packed.contract(flat).tensor, want)
+    assert np.array_equal(plain.contract(flat).tensor, want)
+    # SAT decision with all inputs unknown on the same instance (scalar root, accumulated over slices)
+    dd, dnet = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
+    dtree = find_tree_elimination(dnet, trials=2, seed=seed)
+    if dtree.width() > target:
+        dtree = dtree.slice_to(target)
+    dec = TreeContraction(CudaFinRel, dd.wiring, tree=dtree, batch_log2=batch)
+    assert bool(dec.contract(dd)) == bool(want.any())
+    if dec.num_slices >= 2:   # a partial slice range and its complement OR to the full answer
+        h = dec.num_slices // 2
+        a = dec.contract(dd, slice_range=(0, h)).tensor | dec.contract(dd, slice_range=(h, dec.num_slices)).tensor
+        assert bool(a) == bool(want.any())
 
 
 def test_kissat_verdicts():
