@@ -204,6 +204,29 @@ static __global__ void k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __
   }
 }
 
+// Packing with an index map: broadcast over wires the source does not have, or re-layout of a packed source.
+template <bool SRC_PACKED>
+__global__ void k_pack_map(const void* __restrict__ src, uint32_t* __restrict__ dst, int64_t n_entries,
+                           const __grid_constant__ BitRuns lo, const __grid_constant__ BitRuns hi) {
+  __shared__ uint32_t lane_off[32];
+  if (threadIdx.x < 32) lane_off[threadIdx.x] = (uint32_t)deposit(lo, (uint64_t)threadIdx.x);
+  __syncthreads();
+  const int64_t n_words = (n_entries + 31) >> 5;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t base = deposit(hi, (uint64_t)w);
+    const int nl = (int)(n_entries - (w << 5) < 32 ? n_entries - (w << 5) : 32);
+    uint32_t bits = 0;
+    for (int e = 0; e < nl; e++) {
+      const uint64_t idx = base + lane_off[e];
+      uint32_t b;
+      if constexpr (SRC_PACKED) b = (((const uint32_t*)src)[idx >> 5] >> (uint32_t)(idx & 31)) & 1u;
+      else b = ((const uint8_t*)src)[idx] != 0;
+      bits |= b << e;
+    }
+    dst[w] = bits;
+  }
+}
+
 static __global__ void k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n_entries,
                                      int accumulate) {
   const int64_t n_vec = (n_entries + 15) >> 4;

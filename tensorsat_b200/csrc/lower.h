@@ -520,6 +520,9 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
 void launch_pack_bits(tsb_ctx* ctx, const void* src_u8, void* dst_bits, int64_t n_entries, cudaStream_t s);
 void launch_unpack_bits(tsb_ctx* ctx, const void* src_bits, void* dst_u8, int64_t n_entries, bool accumulate,
                         cudaStream_t s);
+// dst bit i = src entry (deposit(hi, i >> 5) + deposit(lo, i & 31)); src is uint8 entries or bit-packed
+void launch_pack_map(tsb_ctx* ctx, const void* src, bool src_packed, void* dst_bits, int64_t n_dst_entries,
+                     const BitRuns& lo, const BitRuns& hi, cudaStream_t s);
 inline size_t packed_bytes(int64_t n_entries) { return (size_t)std::max<int64_t>(16, (n_entries + 7) / 8); }
 
 bool merge_wide_supported(const MergeDesc& d, const void* l, int dl, const void* r, int dr, const void* o);

@@ -25,6 +25,18 @@ void launch_pack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entrie
   TSB_CUDA(cudaGetLastError());
 }
 
+void launch_pack_map(tsb_ctx* ctx, const void* src, bool src_packed, void* dst, int64_t n_entries, const BitRuns& lo,
+                     const BitRuns& hi, cudaStream_t stream) {
+  const int64_t n_words = (n_entries + 31) >> 5;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_words + 255) / 256, (int64_t)ctx->sm_count * 16));
+  if (src_packed)
+    TSB_LAUNCH(k_pack_map<true>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
+  else
+    TSB_LAUNCH(k_pack_map<false>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
 void launch_unpack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entries, bool accumulate,
                         cudaStream_t stream) {
   const int64_t n_vec = (n_entries + 15) >> 4;

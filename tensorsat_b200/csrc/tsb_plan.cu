@@ -61,7 +61,7 @@ struct PNode {
   }
 };
 
-enum OpKind { OP_LEAF = 0, OP_STEP = 1, OP_FINAL_PERMUTE = 2, OP_PACK = 3, OP_UNPACK = 4 };
+enum OpKind { OP_LEAF = 0, OP_STEP = 1, OP_FINAL_PERMUTE = 2, OP_PACK = 3, OP_UNPACK = 4, OP_EXPAND = 5 };
 
 struct POp {
   int kind = OP_STEP;
@@ -71,6 +71,8 @@ struct POp {
   bool use_gemm = false;  // lowered at run time: transposes + tcgen05 int8 GEMM
   bool use_bits = false;  // both operands and the result are bit-packed: k_merge_bits
   double alg_bytes_u8 = 0;  // algorithmic bytes at one byte per boolean entry
+  bool cv_map = false;      // conversion with an index map (broadcast over missing wires / packed source)
+  BitRuns cv_lo{}, cv_hi{}; // destination lane (bits 0..4) / word index -> source entry offset
   MergeDesc md{};
   // generic description (wires + extents) used when the merge kernel does not apply
   std::vector<int32_t> lw, rw, ow;
@@ -494,81 +496,132 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
 
   // ---- bit-packed representation for the boolean semiring -----------------------------
   // A step that touches a tensor of >= 2^kPackMinLog2 entries runs on bit-packed operands (k_merge_bits):
-  // 8x fewer bytes on the steps that are HBM-bound.  Conversions (k_pack_bits / k_unpack_bits) are
-  // inserted where a tensor crosses between the two representations; by construction they fall on small
-  // tensors (the leaves' side of the tree and the gathered tail), except around GEMM-lowered steps.
+  // 8x fewer bytes on the steps that are HBM-bound.  Conversions are inserted where a tensor crosses between
+  // the two representations; by construction they fall on small tensors (the leaves' side of the tree and the
+  // gathered tail), except around GEMM-lowered steps.  A small operand is additionally stored BROADCAST over
+  // those of the consumer's five lowest output wires it does not depend on, so that inside the hot kernel
+  // every operand word is a plain load (no in-word lane expansion).
   if (P.mode == TSB_SAT && !force_generic && !(P.flags & TSB_PLAN_NO_PACK)) {
     // test knob: TSB_PACK_MIN_LOG2 lowers the threshold so that small parity cases take the packed path
     const char* env_min = std::getenv("TSB_PACK_MIN_LOG2");
     const double kPackMinLog2 = env_min ? std::atof(env_min) : 20.0;
+    const char* env_exp = std::getenv("TSB_PACK_EXPAND_LOG2");
+    const double kExpandMaxLog2 = env_exp ? std::atof(env_exp) : 27.0;  // broadcast twins stay L2-sized
     const int NN0 = (int)P.nodes.size();
+    auto bits_desc = [&](POp& op) {
+      BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
+      BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
+      BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
+      return make_merge_desc(lb, &rb, ob, false, 7);
+    };
     for (auto& op : P.ops) {
       if (op.kind != OP_STEP || !op.use_merge) continue;
       if (P.stack_out && op.out == P.root) continue;
       const double big = std::max({(double)prod_ext(op.lw, P.wext), (double)prod_ext(op.rw, P.wext),
                                    (double)prod_ext(op.ow, P.wext)});
       if (std::log2(big) < kPackMinLog2) continue;
-      BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
-      BitLabels rb = bit_labels(op.rw.data(), (int)op.rw.size(), P.wext.data());
-      BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
-      MergeArgs m = make_merge_desc(lb, &rb, ob, false, 7);
+      MergeArgs m = bits_desc(op);
       if (!m.ok || m.d.kbits > 8) continue;
       op.use_bits = true;
       op.md = m.d;
     }
-    std::vector<char> made_packed(NN0, 0), needs_packed(NN0, 0), needs_bytes(NN0, 0);
-    for (auto& op : P.ops) {
-      if (op.use_bits) {
-        made_packed[op.out] = 1;
-        needs_packed[op.lhs] = needs_packed[op.rhs] = 1;
-      } else {
-        if (op.lhs >= 0) needs_bytes[op.lhs] = 1;
-        if (op.rhs >= 0) needs_bytes[op.rhs] = 1;
-      }
+    std::vector<char> made_packed(NN0, 0);
+    std::vector<int> consumer(NN0, -1);
+    for (int oi = 0; oi < (int)P.ops.size(); oi++) {
+      const POp& op = P.ops[oi];
+      if (op.use_bits) made_packed[op.out] = 1;
+      if (op.lhs >= 0) consumer[op.lhs] = oi;
+      if (op.rhs >= 0) consumer[op.rhs] = oi;
     }
+    std::vector<int> prod_rep(NN0), cons_rep(NN0);
+    std::vector<std::vector<POp>> after(NN0);  // conversions emitted right after the producer of a node
+    for (int i = 0; i < NN0; i++) prod_rep[i] = cons_rep[i] = i;
     for (int i = 0; i < NN0; i++) {
-      const PNode& nd = P.nodes[i];
-      if (nd.is_out || nd.gathered || i == P.root) needs_bytes[i] = 1;
+      const bool role = P.nodes[i].is_out || P.nodes[i].gathered || i == P.root;  // bytes must exist in node i
+      const bool Pp = made_packed[i] != 0;
+      const bool Cp = consumer[i] >= 0 && P.ops[consumer[i]].use_bits;
+      if (!Pp && !Cp) continue;
+      const bool bytes_in_i = !Pp || role || (consumer[i] >= 0 && !Cp);
+      if (Pp) {
+        if (bytes_in_i) {  // the step writes a packed temporary that is unpacked into node i
+          PNode t = P.nodes[i];
+          t.packed = true; t.is_out = false; t.gathered = false; t.offset = -1;
+          prod_rep[i] = (int)P.nodes.size();
+          P.nodes.push_back(t);
+          POp cv;
+          cv.kind = OP_UNPACK; cv.lhs = prod_rep[i]; cv.out = i;
+          cv.per_slice = !P.nodes[i].shared;
+          after[i].push_back(cv);
+        } else {
+          P.nodes[i].packed = true;
+        }
+      }
+      if (!Cp) continue;
+      // wires of the consumer's five lowest output positions this operand does not hold
+      POp& z = P.ops[consumer[i]];
+      const bool is_lhs = z.lhs == i;
+      const std::vector<int32_t>& zw = is_lhs ? z.lw : z.rw;
+      std::vector<int32_t> add;
+      for (int q = (int)z.ow.size() - 5; q < (int)z.ow.size(); q++) {
+        if (q < 0) continue;
+        if (std::find(zw.begin(), zw.end(), z.ow[q]) == zw.end()) add.push_back(z.ow[q]);
+      }
+      const PNode src = P.nodes[i];
+      if (!add.empty() && std::log2((double)src.stored_numel()) + (double)add.size() > kExpandMaxLog2) add.clear();
+      if (add.empty() && src.packed) continue;  // read as is
+      PNode t = src;
+      t.packed = true; t.is_out = false; t.offset = -1;
+      if (t.gathered) { t.gathered = false; t.shared = true; t.post = true; }  // converted once, after the slice loop
+      {
+        std::set<int32_t> rs(t.reg.begin(), t.reg.end());
+        rs.insert(add.begin(), add.end());
+        t.reg = order_reg(rs);
+        t.reg_numel = prod_ext(t.reg, P.wext);
+      }
+      cons_rep[i] = (int)P.nodes.size();
+      P.nodes.push_back(t);
+      POp cv;
+      cv.kind = src.packed ? OP_EXPAND : OP_PACK;
+      cv.lhs = i; cv.out = cons_rep[i];
+      cv.per_slice = !t.shared;
+      if (!add.empty() || src.packed) {
+        // dst entry index -> src entry index (bits 0..4 of dst: lanes of one word; the rest: word index)
+        const std::vector<int32_t> dw = t.stored(), sw = src.stored();
+        BitLabels db = bit_labels(dw.data(), (int)dw.size(), P.wext.data());
+        BitLabels sb = bit_labels(sw.data(), (int)sw.size(), P.wext.data());
+        auto sp = positions(sb);
+        const int nd = (int)db.size();
+        for (int j = 0; j < nd; j++) {
+          auto it = sp.find(db[nd - 1 - j]);
+          if (it == sp.end()) continue;
+          if (j < 5) runs_add(cv.cv_lo, j, it->second);
+          else runs_add(cv.cv_hi, j - 5, it->second);
+        }
+        cv.cv_map = true;
+      }
+      after[i].push_back(cv);
+      // the consumer sees the broadcast operand
+      (is_lhs ? z.lw : z.rw) = P.nodes[z.out].shared ? t.stored() : t.reg;
     }
-    std::vector<int> twin(NN0, -1);  // id of the packed version when the node itself stays in bytes
     std::vector<POp> ops2;
     ops2.reserve(P.ops.size() + 64);
-    auto packed_id = [&](int i) { return P.nodes[i].packed ? i : twin[i]; };
-    for (int i = 0; i < NN0; i++) {
-      if (made_packed[i] && !needs_bytes[i]) { P.nodes[i].packed = true; continue; }
-      if (!(made_packed[i] ? true : needs_packed[i])) continue;
-      // a second node holding the packed version
-      PNode t = P.nodes[i];
-      t.packed = true;
-      t.is_out = false;
-      t.offset = -1;
-      if (!made_packed[i] && t.gathered) { t.gathered = false; t.shared = true; t.post = true; }  // packed after the loop
-      if (made_packed[i]) t.gathered = false;  // plain per-slice temporary, unpacked into the gathered block
-      twin[i] = (int)P.nodes.size();
-      P.nodes.push_back(t);
-    }
     for (auto& op0 : P.ops) {
       POp op = op0;
       const int y = op.out;
       if (op.use_bits) {
-        op.lhs = packed_id(op.lhs);
-        op.rhs = packed_id(op.rhs);
-        op.out = packed_id(y);
+        op.lhs = cons_rep[op.lhs];
+        op.rhs = cons_rep[op.rhs];
+        op.out = prod_rep[y];
+        MergeArgs m = bits_desc(op);  // operand wire lists may have grown
+        TSB_CHECK(m.ok && m.d.kbits <= 8, TSB_ERR_INVALID, "internal: broadcast operand broke the merge order");
+        op.md = m.d;
         op.alg_bytes = op.alg_bytes_u8 / 8.0;
+        P.info.n_packed_steps++;
       }
       ops2.push_back(op);
-      if (twin[y] < 0) continue;
-      POp cv;
-      cv.kind = made_packed[y] ? OP_UNPACK : OP_PACK;
-      cv.lhs = made_packed[y] ? twin[y] : y;
-      cv.out = made_packed[y] ? y : twin[y];
-      cv.per_slice = !P.nodes[cv.out].shared;
-      cv.alg_bytes = 0;  // representation change, not algorithmic work
-      ops2.push_back(cv);
-      P.info.n_conversions++;
+      for (auto& cv : after[y]) { ops2.push_back(cv); P.info.n_conversions++; }
     }
     P.ops.swap(ops2);
-    for (auto& op : P.ops) if (op.use_bits) P.info.n_packed_steps++;
   }
   const int NN = (int)P.nodes.size();  // tree nodes + packed twins (the stacked result buffer comes later)
 
@@ -775,11 +828,15 @@ int64_t shared_offset(const tsb_plan& P, const PNode& nd, const std::vector<int6
 void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vector<int64_t>* digits, bool accumulate,
               cudaStream_t stream) {
   tsb_ctx* ctx = P.ctx;
-  if (op.kind == OP_PACK || op.kind == OP_UNPACK) {
+  if (op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND) {
     const PNode& src = P.nodes[op.lhs];
     const PNode& dst = P.nodes[op.out];
-    if (op.kind == OP_PACK) {
-      launch_pack_bits(ctx, base + src.offset, base + dst.offset, src.stored_numel(), stream);
+    if (op.kind != OP_UNPACK) {
+      if (op.cv_map)
+        launch_pack_map(ctx, base + src.offset, op.kind == OP_EXPAND, base + dst.offset, dst.stored_numel(), op.cv_lo,
+                        op.cv_hi, stream);
+      else
+        launch_pack_bits(ctx, base + src.offset, base + dst.offset, src.stored_numel(), stream);
       return;
     }
     void* pd = dst.is_out ? out_ptr : (void*)(base + dst.offset);
@@ -886,7 +943,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     if (!first) os << ",";
     first = false;
     const PNode& o = plan->nodes[op.out];
-    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
+    os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
        << ",\"small\":" << (op.small ? 1 : 0) << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR

@@ -448,6 +448,71 @@ def test_bit_packed_plans_give_the_same_solution_tensors(monkeypatch, k, n, m, s
         assert bool(a) == bool(want.any())
 
 
+@pytest.mark.parametrize("n,m,seed,batch,n_out", [(22, 90, 6, 13, 6), (22, 92, 2, 11, 9), (24, 100, 6, 15, 5), (24, 96, 4, 12, 7)])
+def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out):
+    """Marginals over a few variables (2^n_out entries, zeros and ones) through sliced plans whose pre, per-slice,
+    gathered and post steps all run bit-packed, with broadcast twins: equal to brute force, to the byte plan, and a
+    partial slice range plus its complement OR to the full answer."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    cnf = CNFInstance.random(3, n, m, rng=seed)
+    flat, net0 = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
+    outs = tuple(int(v) for v in np.linspace(0, n - 1, n_out).astype(int))
+    net = Network(net0.inputs, outs, net0.size_dict)
+    tree = find_tree_elimination(net, trials=2, seed=seed)
+    tree = tree.slice_to(max(tree.width() - 3, n_out + 2))
+    assert tree.num_slices >= 2
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    want = brute.any(axis=tuple(v for v in range(n) if v not in outs)).astype(np.uint8)
+    assert 0 < np.count_nonzero(want) < want.size
+    leaves = [_native.upload(b.tensor.astype(np.uint8)) for b in flat.boxes]
+    got = {}
+    for flags in (0, _native.PLAN_NO_PACK):
+        plan = _native.Plan(net.inputs, outs, net.size_dict, tree.ssa_path, tree.sliced_wires, mode=_native.MODE_SAT,
+                            batch_log2=batch, flags=flags)
+        assert (plan.info["n_packed_steps"] > 0) == (flags == 0)
+        res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
+        plan.execute(leaves, res)
+        got[flags] = res.cpu().numpy().reshape(want.shape).copy()
+        h = plan.info["n_slices"] // 2
+        a, b = torch.zeros_like(res), torch.zeros_like(res)
+        plan.execute(leaves, a, 0, h)
+        plan.execute(leaves, b, h, plan.info["n_slices"])
+        assert np.array_equal((a | b).cpu().numpy().reshape(want.shape), want)
+    assert np.array_equal(got[0], want) and np.array_equal(got[_native.PLAN_NO_PACK], want)
+
+
+def test_assignment_search_on_bit_packed_sliced_plan(monkeypatch):
+    """The reference's assignment search (notebooks/02-random-ksat.ipynb:707-722) on one sliced, bit-packed
+    plan whose leaves change between executions: every decision must agree with brute force, and the model
+    found must satisfy the formula."""
+    monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    n, m, seed = 24, 100, 6
+    cnf = CNFInstance.random(3, n, m, rng=seed)
+    wiring = cnf.contraction_wiring()
+    tree = find_tree_elimination(Network.from_wiring(wiring), trials=2, seed=0)
+    tree = tree.slice_to(tree.width() - 2)
+    c = TreeContraction(CudaFinRel, wiring, tree=tree, batch_log2=13)
+    kinds = {(o["kind"], o["per_slice"], o["post"]) for o in c.plan().describe()["ops"]}
+    assert {("bits", 1, 0), ("bits", 0, 1), ("pack", 0, 1), ("unpack", 1, 0), ("expand", 1, 0)} <= kinds and c.num_slices == 4
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    assert brute.any()
+    prefix = ""
+    for _ in range(n):
+        for bit in "01":
+            spec = prefix + bit + "?" * (n - len(prefix) - 1)
+            got = bool(c.contract((cnf.inputs(spec) >> cnf.diagram()).flatten()))
+            want = bool(brute[tuple(int(ch) for ch in prefix + bit)].any())
+            assert got == want, spec
+            if got:
+                prefix += bit
+                break
+    assert brute[tuple(int(ch) for ch in prefix)] == 1
+
+
 def test_kissat_verdicts():
     """examples/test_sat_solver.py:22-190 through the DIMACS parser and the plan executor."""
     import os
