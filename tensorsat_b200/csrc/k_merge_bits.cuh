@@ -94,7 +94,10 @@ TSB_D void bits_fetch(const uint32_t* __restrict__ base, uint64_t a, const BitsL
 
 // d.nibL / d.nibR hold 7-bit lane masks, d.n_vec = 2^(R-7), all operand offsets are in entries (= bits).
 // bitoffL / bitoffR: where the operand (a slice of a shared tensor) starts inside lhs / rhs.
-__global__ void __launch_bounds__(kBitsThreads, 4)
+// KB = 0 / 1: that many summed wires, every load of a thread's vectors issued before the first use
+// (the steps of a SAT plan sum at most one wire); KB = -1: loop over the 2^kbits combinations.
+template <int KB>
+__global__ void __launch_bounds__(kBitsThreads, KB == 1 ? 3 : 4)
 k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ lhs, uint64_t bitoffL,
              const uint32_t* __restrict__ rhs, uint64_t bitoffR, uint4* __restrict__ out) {
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
@@ -119,9 +122,9 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
   runs_to_smem(d.hiR, runsR);
   __syncthreads();
   const BitsLane lnL = bits_lane(d.nibL), lnR = bits_lane(d.nibR);
-  const int K = 1 << d.kbits;
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const bool acc_out = d.accumulate != 0, has_rhs = d.has_rhs != 0;
+  const uint64_t sl1 = (uint64_t)d.ksL[0], sr1 = (uint64_t)d.ksR[0];  // KB == 1: stride of the summed wire
   int64_t tile = blockIdx.x;
   uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
   uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
@@ -153,24 +156,52 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
             acc[g][0] = p.x; acc[g][1] = p.y; acc[g][2] = p.z; acc[g][3] = p.w;
           }
       }
-      for (int kk = 0; kk < K; kk++) {
-        const uint64_t sl = (uint64_t)kL[kk], sr = (uint64_t)kR[kk];
-        uint32_t XL[kBitsG][4], XR[kBitsG][4];
+      if constexpr (KB >= 0) {
+        constexpr int KK = 1 << KB;
+        uint32_t XL[kBitsG][KK][4], XR[kBitsG][KK][4];
 #pragma unroll
         for (int g = 0; g < kBitsG; g++) {
-          if (on[g]) {
-            bits_fetch(lhs, aL[g] + sl, lnL, lutL, XL[g]);
-            if (has_rhs) bits_fetch(rhs, aR[g] + sr, lnR, lutR, XR[g]);
-            else XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0xffffffffu;
-          } else {
-            XL[g][0] = XL[g][1] = XL[g][2] = XL[g][3] = 0;
-            XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0;
+#pragma unroll
+          for (int kk = 0; kk < KK; kk++) {
+            if (on[g]) {
+              bits_fetch(lhs, aL[g] + (kk ? sl1 : 0), lnL, lutL, XL[g][kk]);
+              if (has_rhs) bits_fetch(rhs, aR[g] + (kk ? sr1 : 0), lnR, lutR, XR[g][kk]);
+              else XR[g][kk][0] = XR[g][kk][1] = XR[g][kk][2] = XR[g][kk][3] = 0xffffffffu;
+            } else {
+              XL[g][kk][0] = XL[g][kk][1] = XL[g][kk][2] = XL[g][kk][3] = 0;
+              XR[g][kk][0] = XR[g][kk][1] = XR[g][kk][2] = XR[g][kk][3] = 0;
+            }
           }
         }
 #pragma unroll
         for (int g = 0; g < kBitsG; g++) {
-          acc[g][0] |= XL[g][0] & XR[g][0]; acc[g][1] |= XL[g][1] & XR[g][1];
-          acc[g][2] |= XL[g][2] & XR[g][2]; acc[g][3] |= XL[g][3] & XR[g][3];
+#pragma unroll
+          for (int kk = 0; kk < KK; kk++) {
+            acc[g][0] |= XL[g][kk][0] & XR[g][kk][0]; acc[g][1] |= XL[g][kk][1] & XR[g][kk][1];
+            acc[g][2] |= XL[g][kk][2] & XR[g][kk][2]; acc[g][3] |= XL[g][kk][3] & XR[g][kk][3];
+          }
+        }
+      } else {
+        const int K = 1 << d.kbits;
+        for (int kk = 0; kk < K; kk++) {
+          const uint64_t sl = (uint64_t)kL[kk], sr = (uint64_t)kR[kk];
+          uint32_t XL[kBitsG][4], XR[kBitsG][4];
+#pragma unroll
+          for (int g = 0; g < kBitsG; g++) {
+            if (on[g]) {
+              bits_fetch(lhs, aL[g] + sl, lnL, lutL, XL[g]);
+              if (has_rhs) bits_fetch(rhs, aR[g] + sr, lnR, lutR, XR[g]);
+              else XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0xffffffffu;
+            } else {
+              XL[g][0] = XL[g][1] = XL[g][2] = XL[g][3] = 0;
+              XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < kBitsG; g++) {
+            acc[g][0] |= XL[g][0] & XR[g][0]; acc[g][1] |= XL[g][1] & XR[g][1];
+            acc[g][2] |= XL[g][2] & XR[g][2]; acc[g][3] |= XL[g][3] & XR[g][3];
+          }
         }
       }
 #pragma unroll

@@ -396,10 +396,11 @@ struct MergeArgs {
 
 // lhs_bits / rhs_bits / out_bits: bit labels MSB first.  Labels of lhs/rhs not in out are summed.
 // Returns ok=false if the monotone-merge preconditions do not hold.
+// allow_broadcast: out labels held by neither operand repeat the value (used to broadcast a packed operand).
 // vbits: output address bits covered by one thread's vector (4 = 16 bytes of uint8 entries, 7 = 16 bytes of
 // bit-packed entries); nibL / nibR are vbits-wide lane masks.
 inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs_bits, const BitLabels& out_bits,
-                                 bool accumulate, int vbits = 4) {
+                                 bool accumulate, int vbits = 4, bool allow_broadcast = false) {
   MergeArgs m;
   const int R = (int)out_bits.size();
   if (R < vbits || R > 62) return m;
@@ -409,8 +410,9 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
   if (rhs_bits) rp = positions(*rhs_bits);
   auto op = positions(out_bits);
   // every out label must come from an operand
-  for (auto& kv : op)
-    if (!lp.count(kv.first) && !rp.count(kv.first)) return m;
+  if (!allow_broadcast)
+    for (auto& kv : op)
+      if (!lp.count(kv.first) && !rp.count(kv.first)) return m;
   // monotone: operand positions strictly increase with out position
   auto monotone = [&](const std::map<int64_t, int>& pp, int& nib, int& nlow) {
     int last = -1;

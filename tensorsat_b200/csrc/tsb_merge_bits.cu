@@ -7,12 +7,19 @@ namespace tsb {
 void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bitoff_l, const void* r,
                        uint64_t bitoff_r, void* o, cudaStream_t stream) {
   TSB_CHECK(d.kbits <= 8, TSB_ERR_UNSUPPORTED, "internal: bit-packed merge with more than 8 summed wires");
-  TSB_CHECK(((uintptr_t)l & 15) == 0 && ((uintptr_t)r & 15) == 0 && ((uintptr_t)o & 15) == 0, TSB_ERR_INVALID,
+  TSB_CHECK(((uintptr_t)l & 15) == 0 && (!d.has_rhs || ((uintptr_t)r & 15) == 0) && ((uintptr_t)o & 15) == 0, TSB_ERR_INVALID,
             "internal: bit-packed operands must be 16-byte aligned");
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
-  TSB_LAUNCH(k_merge_bits, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
-             (const uint32_t*)r, bitoff_r, (uint4*)o);
+  if (d.kbits == 0)
+    TSB_LAUNCH(k_merge_bits<0>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+               (const uint32_t*)r, bitoff_r, (uint4*)o);
+  else if (d.kbits == 1)
+    TSB_LAUNCH(k_merge_bits<1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+               (const uint32_t*)r, bitoff_r, (uint4*)o);
+  else
+    TSB_LAUNCH(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+               (const uint32_t*)r, bitoff_r, (uint4*)o);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
 }

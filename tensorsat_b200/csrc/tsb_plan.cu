@@ -584,11 +584,17 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       cv.kind = src.packed ? OP_EXPAND : OP_PACK;
       cv.lhs = i; cv.out = cons_rep[i];
       cv.per_slice = !t.shared;
-      if (!add.empty() || src.packed) {
+      const std::vector<int32_t> dw = t.stored(), sw = src.stored();
+      BitLabels db = bit_labels(dw.data(), (int)dw.size(), P.wext.data());
+      BitLabels sb = bit_labels(sw.data(), (int)sw.size(), P.wext.data());
+      if (src.packed && db.size() >= 7) {
+        // packed -> packed broadcast = a one-operand merge whose missing output wires repeat the value
+        MergeArgs bm = make_merge_desc(sb, nullptr, db, false, 7, true);
+        TSB_CHECK(bm.ok && bm.d.kbits == 0, TSB_ERR_INVALID, "internal: broadcast twin is not a monotone merge");
+        cv.md = bm.d;
+        cv.use_bits = true;
+      } else if (!add.empty() || src.packed) {
         // dst entry index -> src entry index (bits 0..4 of dst: lanes of one word; the rest: word index)
-        const std::vector<int32_t> dw = t.stored(), sw = src.stored();
-        BitLabels db = bit_labels(dw.data(), (int)dw.size(), P.wext.data());
-        BitLabels sb = bit_labels(sw.data(), (int)sw.size(), P.wext.data());
         auto sp = positions(sb);
         const int nd = (int)db.size();
         for (int j = 0; j < nd; j++) {
@@ -832,7 +838,9 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     const PNode& src = P.nodes[op.lhs];
     const PNode& dst = P.nodes[op.out];
     if (op.kind != OP_UNPACK) {
-      if (op.cv_map)
+      if (op.use_bits)
+        launch_merge_bits(ctx, op.md, base + src.offset, 0, nullptr, 0, base + dst.offset, stream);
+      else if (op.cv_map)
         launch_pack_map(ctx, base + src.offset, op.kind == OP_EXPAND, base + dst.offset, dst.stored_numel(), op.cv_lo,
                         op.cv_hi, stream);
       else
