@@ -181,6 +181,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pack", action="store_true", help="keep boolean intermediates at one byte per entry (A/B runs)")
+    ap.add_argument("--batch-log2", type=int, default=None, help="override the plan's once-only size limit (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
@@ -205,7 +206,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cnf, diagram, tree = load_tree()
-    contraction = TreeContraction(CudaFinRel, diagram.wiring, tree=tree, bit_packing=not args.no_pack)
+    contraction = TreeContraction(CudaFinRel, diagram.wiring, tree=tree, bit_packing=not args.no_pack, batch_log2=-1 if args.batch_log2 is None else args.batch_log2)
     plan = contraction.plan()
     n_slices = plan.info["n_slices"]
     lo, hi = slice_block(n_slices, rank, world)

@@ -175,6 +175,7 @@ typedef struct {
 #define TSB_PLAN_FORCE_GENERIC 2u /* use only the generic kernel (parity reference on device) */
 #define TSB_PLAN_NO_GEMM 4u      /* never lower a step to the tcgen05 GEMM */
 #define TSB_PLAN_NO_PACK 8u      /* keep every boolean intermediate at one byte per entry (no bit-packing) */
+#define TSB_PLAN_NO_FUSE 16u     /* one launch per tree step (no fused n-ary steps) */
 
 typedef struct {
   int64_t n_slices;
@@ -194,6 +195,8 @@ typedef struct {
   double alg_bytes_u8_per_slice; /* alg_bytes_* count the representation the plan uses (1/8 byte when bit-packed) */
   int32_t n_packed_steps;     /* steps executed on bit-packed operands */
   int32_t n_conversions;      /* byte <-> bit conversion launches (per execution of every op once) */
+  int32_t n_fused_steps;      /* tree steps folded into the launch of their consumer (their result is never stored) */
+  int32_t reserved;
 } tsb_plan_info_t;
 
 int tsb_plan_create(tsb_ctx* ctx, const tsb_plan_desc* desc, tsb_plan** plan);

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtsb.so")
 
 TSB_U8, TSB_I32, TSB_I64 = 0, 1, 2
 MODE_SAT, MODE_COUNT = 0, 1
-PLAN_NO_GRAPH, PLAN_FORCE_GENERIC, PLAN_NO_GEMM, PLAN_NO_PACK = 1, 2, 4, 8
+PLAN_NO_GRAPH, PLAN_FORCE_GENERIC, PLAN_NO_GEMM, PLAN_NO_PACK, PLAN_NO_FUSE = 1, 2, 4, 8, 16
 
 _STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: MemoryError, 4: NotImplementedError, 5: OverflowError}
 
@@ -77,6 +77,8 @@ class PlanInfo(C.Structure):
         ("alg_bytes_u8_per_slice", C.c_double),
         ("n_packed_steps", C.c_int32),
         ("n_conversions", C.c_int32),
+        ("n_fused_steps", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -76,6 +76,28 @@ struct MergeDesc {
   int64_t n_vec;      // 2^(R-4)
 };
 
+// descriptor of the fused n-ary bit-packed merge (k_merge_bits.cuh: k_merge_bits_n)
+constexpr int kBitsMaxOps = 4;
+constexpr int kBitsMaxKB = 3;
+
+struct BitsOperand {
+  BitRuns lo, hi;               // vector-in-tile index / tile index -> operand offset (entries)
+  int64_t ks[kBitsMaxKB];       // operand stride of each summed wire (0: operand does not hold it)
+  int32_t hi2;                  // which of output bits 5, 6 the operand holds
+  int32_t pad;
+};
+
+struct BitsNDesc {
+  int32_t R, kbits, n_ops, tile_bits;
+  int64_t n_vec;
+  BitsOperand op[kBitsMaxOps];
+};
+
+struct BitsNPtrs {
+  const uint32_t* p[kBitsMaxOps];
+  uint64_t bitoff[kBitsMaxOps];
+};
+
 template <typename T> struct VecLoad;
 
 TSB_D void load_sub_u8(const uint8_t* p, int vbits, uint32_t buf[4]) {

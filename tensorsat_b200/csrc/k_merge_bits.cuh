@@ -45,13 +45,21 @@ TSB_HD BitsLane bits_lane(int nib7) {
   return l;
 }
 
-// lut[t * 256 + b]: the 32 in-word lanes produced by byte t of a sub-chunk whose value is b
-TSB_D void bits_build_lut(int nib7, uint32_t* lut) {
+// lut[t * 256 + b]: the 32 in-word lanes produced by byte t of a sub-chunk whose value is b.
+// Built once per CTA and only as far as the kernel will index it (nothing when the operand holds all five
+// in-word lanes, table 0 only when it holds at most three).  `pos` is 32 words of shared scratch.
+TSB_D void bits_build_lut(int nib7, uint32_t* lut, uint32_t* pos) {
   const int lo5 = nib7 & 31;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+  const int c5 = __popc((unsigned)lo5);
+  if (threadIdx.x < 32) pos[threadIdx.x] = (uint32_t)pext_bits(threadIdx.x, lo5, 5);
+  __syncthreads();
+  if (c5 == 5) return;
+  const int n = c5 == 4 ? 512 : (1 << (1 << c5));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const uint32_t v = (uint32_t)(i & 255) << (8 * (i >> 8));
     uint32_t x = 0;
-    for (int e = 0; e < 32; e++) x |= ((v >> pext_bits(e, lo5, 5)) & 1u) << e;
+#pragma unroll 8
+    for (int e = 0; e < 32; e++) x |= ((v >> pos[e]) & 1u) << e;
     lut[i] = x;
   }
 }
@@ -102,7 +110,7 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
              const uint32_t* __restrict__ rhs, uint64_t bitoffR, uint4* __restrict__ out) {
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
   __shared__ int64_t kL[256], kR[256];
-  __shared__ uint32_t lutL[512], lutR[512];
+  __shared__ uint32_t lutL[512], lutR[512], posL[32], posR[32];
   __shared__ RunsSmem runsL, runsR;
   const int nt = 1 << d.tile_bits;
   for (int i = threadIdx.x; i < nt; i += kBitsThreads) {
@@ -116,8 +124,8 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
     kL[i] = a;
     kR[i] = b;
   }
-  bits_build_lut(d.nibL, lutL);
-  bits_build_lut(d.nibR, lutR);
+  bits_build_lut(d.nibL, lutL, posL);
+  if (d.has_rhs) bits_build_lut(d.nibR, lutR, posR);
   runs_to_smem(d.hiL, runsL);
   runs_to_smem(d.hiR, runsR);
   __syncthreads();
@@ -206,6 +214,172 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
       }
 #pragma unroll
       for (int g = 0; g < kBitsG; g++)
+        if (on[g]) outp[v0 + g * kBitsThreads] = make_uint4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+    }
+    tile = next;
+  }
+}
+
+// ---- word-aligned fast path ---------------------------------------------------------------------------
+// Both operands hold all five in-word lanes (true for every large step of a plan once small operands are
+// stored broadcast, see tsb_plan.cu): every offset is a multiple of 32 entries, so the kernel works in
+// 32-bit WORD offsets, the word-level lane masks HL / HR (output bits 5, 6) are template parameters and an
+// operand fetch is exactly one 4 / 8 / 16-byte load whose words are used in place.
+template <int H>
+TSB_D void bits_load_words(const uint32_t* __restrict__ p, uint32_t X[4]) {
+  if constexpr (H == 0) { const uint32_t t = *p; X[0] = X[1] = X[2] = X[3] = t; }
+  else if constexpr (H == 1) { const uint2 t = *(const uint2*)p; X[0] = t.x; X[1] = t.y; X[2] = t.x; X[3] = t.y; }
+  else if constexpr (H == 2) { const uint2 t = *(const uint2*)p; X[0] = X[1] = t.x; X[2] = X[3] = t.y; }
+  else { const uint4 t = *(const uint4*)p; X[0] = t.x; X[1] = t.y; X[2] = t.z; X[3] = t.w; }
+}
+
+template <int KB, int HL, int HR>
+__global__ void __launch_bounds__(kBitsThreads, 4)
+k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ lhs, uint64_t bitoffL,
+               const uint32_t* __restrict__ rhs, uint64_t bitoffR, uint4* __restrict__ out) {
+  constexpr int KK = 1 << KB;
+  constexpr int G = KB == 0 ? 4 : 2;  // eight operand fetches in flight per thread either way
+  __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
+  __shared__ RunsSmem runsL, runsR;
+  const int nt = 1 << d.tile_bits;
+  for (int i = threadIdx.x; i < nt; i += kBitsThreads) {
+    tabL[i] = (uint32_t)(deposit(d.loL, (uint64_t)i) >> 5);
+    tabR[i] = (uint32_t)(deposit(d.loR, (uint64_t)i) >> 5);
+  }
+  runs_to_smem(d.hiL, runsL);
+  runs_to_smem(d.hiR, runsR);
+  __syncthreads();
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const bool acc_out = d.accumulate != 0;
+  const uint64_t kwL = KB ? (uint64_t)d.ksL[0] >> 5 : 0, kwR = KB ? (uint64_t)d.ksR[0] >> 5 : 0;
+  int64_t tile = blockIdx.x;
+  uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
+  uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
+  while (tile < n_tiles) {
+    const uint32_t* pL = lhs + ((bitoffL + offL) >> 5);
+    const uint32_t* pR = rhs + ((bitoffR + offR) >> 5);
+    uint4* outp = out + (tile << d.tile_bits);
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {
+      offL = deposit_warp(runsL, (uint64_t)next);
+      offR = deposit_warp(runsR, (uint64_t)next);
+    }
+    for (int v0 = threadIdx.x; v0 < nt; v0 += kBitsThreads * G) {
+      uint32_t XL[G][KK][4], XR[G][KK][4];
+      bool on[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int vi = v0 + g * kBitsThreads;
+        on[g] = vi < nt;
+        const uint32_t* ql = pL + tabL[on[g] ? vi : 0];
+        const uint32_t* qr = pR + tabR[on[g] ? vi : 0];
+#pragma unroll
+        for (int kk = 0; kk < KK; kk++) {
+          bits_load_words<HL>(ql + (kk ? kwL : 0), XL[g][kk]);
+          bits_load_words<HR>(qr + (kk ? kwR : 0), XR[g][kk]);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        if (!on[g]) continue;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (acc_out) r = outp[v0 + g * kBitsThreads];
+#pragma unroll
+        for (int kk = 0; kk < KK; kk++) {
+          r.x |= XL[g][kk][0] & XR[g][kk][0]; r.y |= XL[g][kk][1] & XR[g][kk][1];
+          r.z |= XL[g][kk][2] & XR[g][kk][2]; r.w |= XL[g][kk][3] & XR[g][kk][3];
+        }
+        outp[v0 + g * kBitsThreads] = r;
+      }
+    }
+    tile = next;
+  }
+}
+
+// ---- fused n-ary merge ("bucket" step) -----------------------------------------------------------------
+// out[o] = OR over the summed wires of AND_i operand_i[...]: several consecutive steps of the tree in ONE
+// pass, so the intermediates between them never reach HBM (classic bucket elimination: multiply every
+// tensor of the bucket, sum the variable out, without materialising the product).  For a chain
+// T1 = sum_k1 X*Y, T2 = sum_k2 T1*Z the fused step reads X, Y, Z and writes T2; T1 (the widest tensor of
+// the plan) is neither written nor read back.  Word-aligned operands only (see k_merge_bits_w).
+TSB_D void bits_load_words_rt(const uint32_t* __restrict__ p, int hi2, uint32_t X[4]) {
+  if (hi2 == 3) { const uint4 t = *(const uint4*)p; X[0] = t.x; X[1] = t.y; X[2] = t.z; X[3] = t.w; }
+  else if (hi2 == 0) { const uint32_t t = *p; X[0] = X[1] = X[2] = X[3] = t; }
+  else {
+    const uint2 t = *(const uint2*)p;
+    if (hi2 == 1) { X[0] = t.x; X[1] = t.y; X[2] = t.x; X[3] = t.y; }
+    else { X[0] = X[1] = t.x; X[2] = X[3] = t.y; }
+  }
+}
+
+template <int NOPS, int KB>
+__global__ void __launch_bounds__(kBitsThreads, 3)
+k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ BitsNPtrs ptrs, uint4* __restrict__ out) {
+  constexpr int KK = 1 << KB;
+  constexpr int G = NOPS <= 3 ? 2 : 1;   // operand fetches in flight per thread: G * NOPS
+  __shared__ uint32_t tab[NOPS][1 << kMergeTileBits];
+  __shared__ uint32_t kw[NOPS][KK];
+  __shared__ RunsSmem runs[NOPS];
+  const int nt = 1 << d.tile_bits;
+#pragma unroll
+  for (int o = 0; o < NOPS; o++) {
+    for (int i = threadIdx.x; i < nt; i += kBitsThreads) tab[o][i] = (uint32_t)(deposit(d.op[o].lo, (uint64_t)i) >> 5);
+    if (threadIdx.x < KK) {
+      int64_t a = 0;
+      for (int q = 0; q < KB; q++)
+        if (threadIdx.x >> q & 1) a += d.op[o].ks[q];
+      kw[o][threadIdx.x] = (uint32_t)(a >> 5);
+    }
+    runs_to_smem(d.op[o].hi, runs[o]);
+  }
+  __syncthreads();
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  int64_t tile = blockIdx.x;
+  uint64_t off[NOPS];
+#pragma unroll
+  for (int o = 0; o < NOPS; o++) off[o] = tile < n_tiles ? deposit_warp(runs[o], (uint64_t)tile) : 0;
+  while (tile < n_tiles) {
+    uint32_t base[NOPS];  // word offset of this tile inside each operand (operands hold < 2^37 entries)
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) base[o] = (uint32_t)((ptrs.bitoff[o] + off[o]) >> 5);
+    uint4* outp = out + (tile << d.tile_bits);
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {
+#pragma unroll
+      for (int o = 0; o < NOPS; o++) off[o] = deposit_warp(runs[o], (uint64_t)next);
+    }
+    for (int v0 = threadIdx.x; v0 < nt; v0 += kBitsThreads * G) {
+      uint32_t q[G][NOPS];
+      bool on[G];
+      uint32_t acc[G][4];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int vi = v0 + g * kBitsThreads;
+        on[g] = vi < nt;
+#pragma unroll
+        for (int o = 0; o < NOPS; o++) q[g][o] = base[o] + tab[o][on[g] ? vi : 0];
+        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < KK; kk++) {
+        uint32_t X[G][NOPS][4];
+#pragma unroll
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int o = 0; o < NOPS; o++) bits_load_words_rt(ptrs.p[o] + (q[g][o] + kw[o][kk]), d.op[o].hi2, X[g][o]);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+          for (int w = 0; w < 4; w++) {
+            uint32_t t = X[g][0][w];
+#pragma unroll
+            for (int o = 1; o < NOPS; o++) t &= X[g][o][w];
+            acc[g][w] |= t;
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++)
         if (on[g]) outp[v0 + g * kBitsThreads] = make_uint4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
     }
     tile = next;

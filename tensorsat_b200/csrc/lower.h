@@ -471,6 +471,70 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
   return m;
 }
 
+// Fused n-ary bit-packed merge: operands[i] / out are bit labels MSB first; every operand must hold the five
+// in-word lanes of the output (plans store small operands broadcast), at most kBitsMaxKB summed labels.
+struct BitsNArgs {
+  BitsNDesc d;
+  bool ok = false;
+};
+
+inline BitsNArgs make_bits_n_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits) {
+  BitsNArgs m;
+  const int R = (int)out_bits.size(), n = (int)operands.size();
+  if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
+  auto op = positions(out_bits);
+  std::vector<std::map<int64_t, int>> lp(n);
+  for (int o = 0; o < n; o++) {
+    if (has_dups(operands[o])) return m;
+    lp[o] = positions(operands[o]);
+  }
+  for (auto& kv : op) {
+    bool found = false;
+    for (int o = 0; o < n; o++) found = found || lp[o].count(kv.first);
+    if (!found) return m;
+  }
+  std::vector<int64_t> ks;
+  for (int o = 0; o < n; o++)
+    for (auto& kv : lp[o])
+      if (!op.count(kv.first) && std::find(ks.begin(), ks.end(), kv.first) == ks.end()) ks.push_back(kv.first);
+  if ((int)ks.size() > kBitsMaxKB) return m;
+  BitsNDesc& d = m.d;
+  d = BitsNDesc{};
+  d.R = R;
+  d.n_ops = n;
+  d.kbits = (int)ks.size();
+  const int vb = R - 7;
+  d.tile_bits = std::min(vb, std::min(kMergeTileBits, std::max(8, vb - 10)));
+  d.n_vec = int64_t(1) << vb;
+  for (int o = 0; o < n; o++) {
+    BitsOperand& bo = d.op[o];
+    int last = -1, nlow = 0, nib = 0;
+    for (int j = 0; j < R; j++) {
+      auto it = lp[o].find(out_bits[R - 1 - j]);
+      if (it == lp[o].end()) continue;
+      if (it->second <= last) return m;
+      last = it->second;
+      if (j < 7) {
+        if (it->second != nlow) return m;
+        nib |= 1 << j;
+        nlow++;
+      } else {
+        const bool lo = (j - 7) < d.tile_bits;
+        runs_add(lo ? bo.lo : bo.hi, lo ? j - 7 : j - 7 - d.tile_bits, it->second);
+      }
+    }
+    if ((nib & 31) != 31) return m;
+    if (operands[o].size() > 36) return m;  // word offsets are 32-bit
+    bo.hi2 = nib >> 5;
+    for (int q = 0; q < d.kbits; q++) bo.ks[q] = lp[o].count(ks[q]) ? int64_t(1) << lp[o][ks[q]] : 0;
+  }
+  m.ok = true;
+  return m;
+}
+
+void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
+                         cudaStream_t s);
+
 #ifdef TSB_MERGE_GENERIC_IMPL
 template <typename TL, typename TR, typename TO>
 inline void launch_merge_t(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void* r, void* o, bool clamp,

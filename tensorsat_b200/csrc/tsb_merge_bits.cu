@@ -4,13 +4,52 @@
 
 namespace tsb {
 
+template <int KB, int HL, int HR>
+static void bits_w_one(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bl, const void* r, uint64_t br, void* o,
+                       int grid, cudaStream_t stream) {
+  auto k = k_merge_bits_w<KB, HL, HR>;
+  TSB_LAUNCH(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bl, (const uint32_t*)r, br, (uint4*)o);
+}
+
+template <int KB, int HL>
+static void bits_w_r(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bl, const void* r, uint64_t br, void* o,
+                     int grid, cudaStream_t s) {
+  switch (d.nibR >> 5) {
+    case 0: bits_w_one<KB, HL, 0>(ctx, d, l, bl, r, br, o, grid, s); break;
+    case 1: bits_w_one<KB, HL, 1>(ctx, d, l, bl, r, br, o, grid, s); break;
+    case 2: bits_w_one<KB, HL, 2>(ctx, d, l, bl, r, br, o, grid, s); break;
+    default: bits_w_one<KB, HL, 3>(ctx, d, l, bl, r, br, o, grid, s); break;
+  }
+}
+
+template <int KB>
+static void bits_w_l(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bl, const void* r, uint64_t br, void* o,
+                     int grid, cudaStream_t s) {
+  switch (d.nibL >> 5) {
+    case 0: bits_w_r<KB, 0>(ctx, d, l, bl, r, br, o, grid, s); break;
+    case 1: bits_w_r<KB, 1>(ctx, d, l, bl, r, br, o, grid, s); break;
+    case 2: bits_w_r<KB, 2>(ctx, d, l, bl, r, br, o, grid, s); break;
+    default: bits_w_r<KB, 3>(ctx, d, l, bl, r, br, o, grid, s); break;
+  }
+}
+
 void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bitoff_l, const void* r,
                        uint64_t bitoff_r, void* o, cudaStream_t stream) {
   TSB_CHECK(d.kbits <= 8, TSB_ERR_UNSUPPORTED, "internal: bit-packed merge with more than 8 summed wires");
   TSB_CHECK(((uintptr_t)l & 15) == 0 && (!d.has_rhs || ((uintptr_t)r & 15) == 0) && ((uintptr_t)o & 15) == 0, TSB_ERR_INVALID,
             "internal: bit-packed operands must be 16-byte aligned");
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
-  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
+  // the general kernel builds its lane tables per CTA: give every CTA a few tiles to amortise that
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + 3) / 4, (int64_t)ctx->sm_count * 8));
+  if (d.has_rhs && d.kbits <= 1 && (d.nibL & 31) == 31 && (d.nibR & 31) == 31) {
+    // word-aligned fast path: both operands hold the five in-word lanes
+    const int gw = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
+    if (d.kbits == 0) bits_w_l<0>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream);
+    else bits_w_l<1>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream);
+    ctx->launches++;
+    TSB_CUDA(cudaGetLastError());
+    return;
+  }
   if (d.kbits == 0)
     TSB_LAUNCH(k_merge_bits<0>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
@@ -20,6 +59,43 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
   else
     TSB_LAUNCH(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
+template <int NOPS, int KB>
+static void bits_n_one(const BitsNDesc& d, const BitsNPtrs& pp, void* o, int grid, cudaStream_t stream) {
+  auto k = k_merge_bits_n<NOPS, KB>;
+  TSB_LAUNCH(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, pp, (uint4*)o);
+}
+
+template <int NOPS>
+static void bits_n_k(tsb_ctx* ctx, const BitsNDesc& d, const BitsNPtrs& pp, void* o, int grid, cudaStream_t stream) {
+  (void)ctx;
+  switch (d.kbits) {
+    case 0: bits_n_one<NOPS, 0>(d, pp, o, grid, stream); break;
+    case 1: bits_n_one<NOPS, 1>(d, pp, o, grid, stream); break;
+    case 2: bits_n_one<NOPS, 2>(d, pp, o, grid, stream); break;
+    default: bits_n_one<NOPS, 3>(d, pp, o, grid, stream); break;
+  }
+}
+
+void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
+                         cudaStream_t stream) {
+  TSB_CHECK(d.n_ops >= 2 && d.n_ops <= kBitsMaxOps && d.kbits >= 0 && d.kbits <= kBitsMaxKB, TSB_ERR_INVALID,
+            "internal: bad fused merge descriptor");
+  BitsNPtrs pp{};
+  for (int i = 0; i < d.n_ops; i++) {
+    TSB_CHECK(((uintptr_t)ptrs[i] & 15) == 0, TSB_ERR_INVALID, "internal: bit-packed operands must be 16-byte aligned");
+    pp.p[i] = (const uint32_t*)ptrs[i];
+    pp.bitoff[i] = bitoffs[i];
+  }
+  TSB_CHECK(((uintptr_t)o & 15) == 0, TSB_ERR_INVALID, "internal: bit-packed result must be 16-byte aligned");
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 6));
+  if (d.n_ops == 2) bits_n_k<2>(ctx, d, pp, o, grid, stream);
+  else if (d.n_ops == 3) bits_n_k<3>(ctx, d, pp, o, grid, stream);
+  else bits_n_k<4>(ctx, d, pp, o, grid, stream);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
 }

@@ -71,6 +71,15 @@ struct POp {
   bool use_gemm = false;  // lowered at run time: transposes + tcgen05 int8 GEMM
   bool use_bits = false;  // both operands and the result are bit-packed: k_merge_bits
   double alg_bytes_u8 = 0;  // algorithmic bytes at one byte per boolean entry
+  std::vector<int> xn;                    // fused step: operands beyond lhs / rhs (node ids) ...
+  std::vector<std::vector<int32_t>> xw;   // ... and their wires
+  int n_fused = 0;                        // tree steps folded into this launch besides its own
+  BitsNDesc nd{};                         // descriptor of a fused step (k_merge_bits_n)
+  int n_operands() const { return kind == OP_STEP ? 2 + (int)xn.size() : 1; }
+  std::vector<int> all_operands() const { std::vector<int> v{lhs, rhs}; v.insert(v.end(), xn.begin(), xn.end()); return v; }
+  int operand(int j) const { return j == 0 ? lhs : j == 1 ? rhs : xn[j - 2]; }
+  const std::vector<int32_t>& operand_wires(int j) const { return j == 0 ? lw : j == 1 ? rw : xw[j - 2]; }
+  std::vector<int32_t>& operand_wires(int j) { return j == 0 ? lw : j == 1 ? rw : xw[j - 2]; }
   bool cv_map = false;      // conversion with an index map (broadcast over missing wires / packed source)
   BitRuns cv_lo{}, cv_hi{}; // destination lane (bits 0..4) / word index -> source entry offset
   MergeDesc md{};
@@ -500,13 +509,16 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   // the two representations; by construction they fall on small tensors (the leaves' side of the tree and the
   // gathered tail), except around GEMM-lowered steps.  A small operand is additionally stored BROADCAST over
   // those of the consumer's five lowest output wires it does not depend on, so that inside the hot kernel
-  // every operand word is a plain load (no in-word lane expansion).
+  // every operand word is a plain load (no in-word lane expansion).  Consecutive packed steps are FUSED into
+  // one n-ary launch (k_merge_bits_n) when the intermediate between them is large: it is then neither
+  // written nor read back (bucket elimination without materialising the product).
   if (P.mode == TSB_SAT && !force_generic && !(P.flags & TSB_PLAN_NO_PACK)) {
-    // test knob: TSB_PACK_MIN_LOG2 lowers the threshold so that small parity cases take the packed path
-    const char* env_min = std::getenv("TSB_PACK_MIN_LOG2");
-    const double kPackMinLog2 = env_min ? std::atof(env_min) : 20.0;
-    const char* env_exp = std::getenv("TSB_PACK_EXPAND_LOG2");
-    const double kExpandMaxLog2 = env_exp ? std::atof(env_exp) : 27.0;  // broadcast twins stay L2-sized
+    // test knobs: thresholds lowered so that small parity cases take these paths
+    auto env_or = [](const char* name, double dflt) { const char* e = std::getenv(name); return e ? std::atof(e) : dflt; };
+    const double kPackMinLog2 = env_or("TSB_PACK_MIN_LOG2", 20.0);
+    const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
+    const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
+    const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
     const int NN0 = (int)P.nodes.size();
     auto bits_desc = [&](POp& op) {
       BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
@@ -525,19 +537,93 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       op.use_bits = true;
       op.md = m.d;
     }
+    auto has_role = [&](int i) { return P.nodes[i].is_out || P.nodes[i].gathered || i == P.root; };
+    // wires of the five lowest output positions of `ow` that the operand does not hold
+    auto missing_low = [&](const std::vector<int32_t>& ow, const std::vector<int32_t>& w) {
+      std::vector<int32_t> add;
+      for (int q = std::max(0, (int)ow.size() - 5); q < (int)ow.size(); q++)
+        if (std::find(w.begin(), w.end(), ow[q]) == w.end()) add.push_back(ow[q]);
+      return add;
+    };
+    // the slice of a broadcast twin a step reads must stay L2-sized; the whole twin (all slices) is written once
+    auto can_broadcast = [&](int node, size_t n_add) {
+      return n_add == 0 || (std::log2((double)P.nodes[node].reg_numel) + (double)n_add <= kExpandMaxLog2 &&
+                            std::log2((double)P.nodes[node].stored_numel()) + (double)n_add <= kExpandMaxLog2 + 4.0);
+    };
+    // ---- fusion ------------------------------------------------------------------------------------------
+    std::vector<char> dead(P.ops.size(), 0);
+    if (kFuseMaxK >= 0) {
+      // candidate edges producer -> consumer, largest intermediate first: the widest tensors are the ones
+      // worth never storing; a fused group is represented by its topmost consumer
+      std::vector<int> producer_op(NN0, -1), absorbed(P.ops.size(), -1);
+      for (int oi = 0; oi < (int)P.ops.size(); oi++) producer_op[P.ops[oi].out] = oi;
+      struct Edge { double lg; int pi, oi; };
+      std::vector<Edge> edges;
+      for (int oi = 0; oi < (int)P.ops.size(); oi++) {
+        const POp& op = P.ops[oi];
+        if (!op.use_bits) continue;
+        for (int j = 0; j < 2; j++) {
+          const int T = op.operand(j);
+          const int pi = producer_op[T];
+          if (pi < 0 || !P.ops[pi].use_bits || has_role(T)) continue;
+          const POp& s1 = P.ops[pi];
+          if (s1.per_slice != op.per_slice || P.nodes[s1.out].post != P.nodes[op.out].post) continue;
+          if (op.operand_wires(j) != s1.ow) continue;
+          const double lg = std::log2((double)prod_ext(s1.ow, P.wext));
+          if (lg >= kFuseMinLog2) edges.push_back({lg, pi, oi});
+        }
+      }
+      std::stable_sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) { return a.lg > b.lg; });
+      auto find_root = [&](int oi) { while (absorbed[oi] >= 0) oi = absorbed[oi]; return oi; };
+      for (const Edge& e : edges) {
+        const int ri = find_root(e.oi);
+        POp& op = P.ops[ri];
+        const POp& s1 = P.ops[e.pi];  // still the root of its own group: its output edge is this one
+        const int T = s1.out;
+        const int n_cur = op.n_operands(), n_s1 = s1.n_operands();
+        int j = -1;
+        for (int q = 0; q < n_cur; q++) if (op.operand(q) == T) j = q;
+        if (j < 0 || n_cur - 1 + n_s1 > kBitsMaxOps) continue;
+        std::vector<int> nodes;
+        std::vector<std::vector<int32_t>> wires;
+        for (int q = 0; q < n_cur; q++)
+          if (q != j) { nodes.push_back(op.operand(q)); wires.push_back(op.operand_wires(q)); }
+        for (int q = 0; q < n_s1; q++) { nodes.push_back(s1.operand(q)); wires.push_back(s1.operand_wires(q)); }
+        std::set<int32_t> summed;
+        bool ok = true;
+        for (size_t q = 0; q < nodes.size() && ok; q++) {
+          for (auto w : wires[q])
+            if (std::find(op.ow.begin(), op.ow.end(), w) == op.ow.end()) summed.insert(w);
+          ok = can_broadcast(nodes[q], missing_low(op.ow, wires[q]).size()) && wires[q].size() <= 36;
+        }
+        if (!ok || (int)summed.size() > std::min(kFuseMaxK, (int)kBitsMaxKB)) continue;
+        // fuse: the producer disappears, its operands join the consumer's launch
+        op.lhs = nodes[0]; op.lw = wires[0];
+        op.rhs = nodes[1]; op.rw = wires[1];
+        op.xn.assign(nodes.begin() + 2, nodes.end());
+        op.xw.assign(wires.begin() + 2, wires.end());
+        op.alg_bytes += s1.alg_bytes;
+        op.alg_bytes_u8 += s1.alg_bytes_u8;
+        op.alg_ops += s1.alg_ops;
+        op.n_fused += 1 + s1.n_fused;
+        dead[e.pi] = 1;
+        absorbed[e.pi] = ri;
+      }
+    }
     std::vector<char> made_packed(NN0, 0);
     std::vector<int> consumer(NN0, -1);
     for (int oi = 0; oi < (int)P.ops.size(); oi++) {
+      if (dead[oi]) continue;
       const POp& op = P.ops[oi];
       if (op.use_bits) made_packed[op.out] = 1;
-      if (op.lhs >= 0) consumer[op.lhs] = oi;
-      if (op.rhs >= 0) consumer[op.rhs] = oi;
+      for (int j = 0; j < op.n_operands(); j++)
+        if (op.operand(j) >= 0) consumer[op.operand(j)] = oi;
     }
     std::vector<int> prod_rep(NN0), cons_rep(NN0);
     std::vector<std::vector<POp>> after(NN0);  // conversions emitted right after the producer of a node
     for (int i = 0; i < NN0; i++) prod_rep[i] = cons_rep[i] = i;
     for (int i = 0; i < NN0; i++) {
-      const bool role = P.nodes[i].is_out || P.nodes[i].gathered || i == P.root;  // bytes must exist in node i
+      const bool role = has_role(i);  // bytes must exist in node i
       const bool Pp = made_packed[i] != 0;
       const bool Cp = consumer[i] >= 0 && P.ops[consumer[i]].use_bits;
       if (!Pp && !Cp) continue;
@@ -557,17 +643,12 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         }
       }
       if (!Cp) continue;
-      // wires of the consumer's five lowest output positions this operand does not hold
       POp& z = P.ops[consumer[i]];
-      const bool is_lhs = z.lhs == i;
-      const std::vector<int32_t>& zw = is_lhs ? z.lw : z.rw;
-      std::vector<int32_t> add;
-      for (int q = (int)z.ow.size() - 5; q < (int)z.ow.size(); q++) {
-        if (q < 0) continue;
-        if (std::find(zw.begin(), zw.end(), z.ow[q]) == zw.end()) add.push_back(z.ow[q]);
-      }
+      int zj = 0;
+      for (int j = 0; j < z.n_operands(); j++) if (z.operand(j) == i) zj = j;
+      std::vector<int32_t> add = missing_low(z.ow, z.operand_wires(zj));
       const PNode src = P.nodes[i];
-      if (!add.empty() && std::log2((double)src.stored_numel()) + (double)add.size() > kExpandMaxLog2) add.clear();
+      if (!can_broadcast(i, add.size())) add.clear();
       if (add.empty() && src.packed) continue;  // read as is
       PNode t = src;
       t.packed = true; t.is_out = false; t.offset = -1;
@@ -607,22 +688,36 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       }
       after[i].push_back(cv);
       // the consumer sees the broadcast operand
-      (is_lhs ? z.lw : z.rw) = P.nodes[z.out].shared ? t.stored() : t.reg;
+      z.operand_wires(zj) = P.nodes[z.out].shared ? t.stored() : t.reg;
     }
     std::vector<POp> ops2;
     ops2.reserve(P.ops.size() + 64);
-    for (auto& op0 : P.ops) {
-      POp op = op0;
+    for (int oi = 0; oi < (int)P.ops.size(); oi++) {
+      if (dead[oi]) continue;
+      POp op = P.ops[oi];
       const int y = op.out;
       if (op.use_bits) {
         op.lhs = cons_rep[op.lhs];
         op.rhs = cons_rep[op.rhs];
+        for (auto& x : op.xn) x = cons_rep[x];
         op.out = prod_rep[y];
-        MergeArgs m = bits_desc(op);  // operand wire lists may have grown
-        TSB_CHECK(m.ok && m.d.kbits <= 8, TSB_ERR_INVALID, "internal: broadcast operand broke the merge order");
-        op.md = m.d;
+        if (op.xn.empty()) {
+          MergeArgs m = bits_desc(op);  // operand wire lists may have grown
+          TSB_CHECK(m.ok && m.d.kbits <= 8, TSB_ERR_INVALID, "internal: broadcast operand broke the merge order");
+          op.md = m.d;
+        } else {
+          std::vector<BitLabels> ol;
+          for (int j = 0; j < op.n_operands(); j++) {
+            const auto& w = op.operand_wires(j);
+            ol.push_back(bit_labels(w.data(), (int)w.size(), P.wext.data()));
+          }
+          BitsNArgs m = make_bits_n_desc(ol, bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data()));
+          TSB_CHECK(m.ok, TSB_ERR_INVALID, "internal: fused step is not a word-aligned monotone merge");
+          op.nd = m.d;
+          P.info.n_fused_steps += op.n_fused;
+        }
         op.alg_bytes = op.alg_bytes_u8 / 8.0;
-        P.info.n_packed_steps++;
+        P.info.n_packed_steps += 1 + op.n_fused;
       }
       ops2.push_back(op);
       for (auto& cv : after[y]) { ops2.push_back(cv); P.info.n_conversions++; }
@@ -640,7 +735,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     if (op.per_slice) continue;
     const bool post = is_post_op(op);
     int w = 0;
-    for (int opnd : {op.lhs, op.rhs})
+    for (int opnd : op.all_operands())
       if (opnd >= 0 && producer[opnd] >= 0) {
         const POp& pr = P.ops[producer[opnd]];
         if (!pr.per_slice && is_post_op(pr) == post) w = std::max(w, pr.wave + 1);
@@ -674,11 +769,11 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   const int T_END = n_pre + n_loop + n_post;
   std::vector<int> last_use(P.nodes.size(), -1);
   for (int i = 0; i < (int)P.ops.size(); i++)
-    for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+    for (int opnd : P.ops[i].all_operands())
       if (opnd >= 0) last_use[opnd] = std::max(last_use[opnd], tpos[i]);
   // shared tensors consumed inside the loop must survive every slice iteration
   for (int i : P.slice_ops)
-    for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+    for (int opnd : P.ops[i].all_operands())
       if (opnd >= 0 && P.nodes[opnd].shared) last_use[opnd] = std::max(last_use[opnd], n_pre + n_loop - 1);
   FreeList fl;
   if (P.mask_root) P.mask_offset = fl.alloc((int64_t)P.nodes[P.root].s_numel);
@@ -714,7 +809,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       }
       std::set<int> freed;
       for (int i : at[t])
-        for (int opnd : {P.ops[i].lhs, P.ops[i].rhs})
+        for (int opnd : P.ops[i].all_operands())
           if (opnd >= 0 && last_use[opnd] == t && P.nodes[opnd].offset >= 0 && !freed.count(opnd)) {
             fl.release(P.nodes[opnd].offset, (int64_t)P.nodes[opnd].bytes);
             freed.insert(opnd);
@@ -724,7 +819,8 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         for (int nd = 0; nd < NN; nd++)
           if (P.nodes[nd].shared && P.nodes[nd].offset >= 0 && last_use[nd] == t && !freed.count(nd)) {
             bool used_here = false;
-            for (int i : at[t]) used_here = used_here || P.ops[i].lhs == nd || P.ops[i].rhs == nd;
+            for (int i : at[t])
+              for (int opnd : P.ops[i].all_operands()) used_here = used_here || opnd == nd;
             if (!used_here) { fl.release(P.nodes[nd].offset, (int64_t)P.nodes[nd].bytes); freed.insert(nd); }
           }
       }
@@ -855,6 +951,18 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
   const PNode& a = P.nodes[op.lhs];
   const PNode& b = P.nodes[op.rhs];
   const PNode& o = P.nodes[op.out];
+  if (op.use_bits && !op.xn.empty()) {
+    // fused n-ary step on packed operands
+    const void* ptrs[kBitsMaxOps];
+    uint64_t offs[kBitsMaxOps];
+    for (int j = 0; j < op.n_operands(); j++) {
+      const PNode& x = P.nodes[op.operand(j)];
+      ptrs[j] = base + x.offset;
+      offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : 0;
+    }
+    launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
+    return;
+  }
   if (op.use_bits) {
     // packed operands: a slice of a shared tensor is addressed by its bit offset
     uint64_t bl = 0, br = 0;
@@ -954,7 +1062,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {

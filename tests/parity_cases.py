@@ -448,8 +448,10 @@ def test_bit_packed_plans_give_the_same_solution_tensors(monkeypatch, k, n, m, s
         assert bool(a) == bool(want.any())
 
 
-@pytest.mark.parametrize("n,m,seed,batch,n_out", [(22, 90, 6, 13, 6), (22, 92, 2, 11, 9), (24, 100, 6, 15, 5), (24, 96, 4, 12, 7)])
-def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out):
+@pytest.mark.parametrize("n,m,seed,batch,n_out,fuse_k", [
+    (22, 90, 6, 13, 6, 2), (22, 92, 2, 11, 9, 2), (24, 100, 6, 15, 5, 2), (24, 96, 4, 12, 7, 2),
+    (22, 90, 6, 13, 6, 3), (22, 92, 2, 11, 9, 3), (22, 92, 2, 11, 9, -1)])
+def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out, fuse_k):
     """Marginals over a few variables (2^n_out entries, zeros and ones) through sliced plans whose pre, per-slice,
     gathered and post steps all run bit-packed, with broadcast twins: equal to brute force, to the byte plan, and a
     partial slice range plus its complement OR to the full answer."""
@@ -458,6 +460,8 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
     from tensorsat_b200 import _native
 
     monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")       # fuse consecutive packed steps whatever their size ...
+    monkeypatch.setenv("TSB_FUSE_MAX_K", str(fuse_k))  # ... up to this many summed wires per launch (-1: never)
     cnf = CNFInstance.random(3, n, m, rng=seed)
     flat, net0 = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
     outs = tuple(int(v) for v in np.linspace(0, n - 1, n_out).astype(int))
@@ -474,6 +478,7 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
         plan = _native.Plan(net.inputs, outs, net.size_dict, tree.ssa_path, tree.sliced_wires, mode=_native.MODE_SAT,
                             batch_log2=batch, flags=flags)
         assert (plan.info["n_packed_steps"] > 0) == (flags == 0)
+        assert (plan.info["n_fused_steps"] > 0) == (flags == 0 and fuse_k >= 0)
         res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
         plan.execute(leaves, res)
         got[flags] = res.cpu().numpy().reshape(want.shape).copy()
@@ -497,7 +502,7 @@ def test_assignment_search_on_bit_packed_sliced_plan(monkeypatch):
     tree = tree.slice_to(tree.width() - 2)
     c = TreeContraction(CudaFinRel, wiring, tree=tree, batch_log2=13)
     kinds = {(o["kind"], o["per_slice"], o["post"]) for o in c.plan().describe()["ops"]}
-    assert {("bits", 1, 0), ("bits", 0, 1), ("pack", 0, 1), ("unpack", 1, 0), ("expand", 1, 0)} <= kinds and c.num_slices == 4
+    assert {("bits", 1, 0), ("bits", 0, 1), ("unpack", 1, 0)} <= kinds and c.num_slices == 4
     brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
     assert brute.any()
     prefix = ""
