@@ -302,33 +302,27 @@ k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__
 // tensor of the bucket, sum the variable out, without materialising the product).  For a chain
 // T1 = sum_k1 X*Y, T2 = sum_k2 T1*Z the fused step reads X, Y, Z and writes T2; T1 (the widest tensor of
 // the plan) is neither written nor read back.  Word-aligned operands only (see k_merge_bits_w).
-TSB_D void bits_load_words_rt(const uint32_t* __restrict__ p, int hi2, uint32_t X[4]) {
-  if (hi2 == 3) { const uint4 t = *(const uint4*)p; X[0] = t.x; X[1] = t.y; X[2] = t.z; X[3] = t.w; }
-  else if (hi2 == 0) { const uint32_t t = *p; X[0] = X[1] = X[2] = X[3] = t; }
-  else {
-    const uint2 t = *(const uint2*)p;
-    if (hi2 == 1) { X[0] = t.x; X[1] = t.y; X[2] = t.x; X[3] = t.y; }
-    else { X[0] = X[1] = t.x; X[2] = X[3] = t.y; }
-  }
-}
-
+// Every operand of a fused step holds all seven lane bits of the output (small operands are stored broadcast
+// over the ones they do not depend on, see tsb_plan.cu), so an operand fetch is one 16-byte load.
 template <int NOPS, int KB>
 __global__ void __launch_bounds__(kBitsThreads, 3)
 k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ BitsNPtrs ptrs, uint4* __restrict__ out) {
   constexpr int KK = 1 << KB;
-  constexpr int G = NOPS <= 3 ? 2 : 1;   // operand fetches in flight per thread: G * NOPS
+  constexpr int G = 2;   // operand fetches in flight per thread: G * NOPS (times KU)
+  constexpr int KU = NOPS * KK <= 8 ? KK : (NOPS <= 2 ? 2 : 1);  // unrolling further only spills
   __shared__ uint32_t tab[NOPS][1 << kMergeTileBits];
   __shared__ uint32_t kw[NOPS][KK];
   __shared__ RunsSmem runs[NOPS];
   const int nt = 1 << d.tile_bits;
 #pragma unroll
   for (int o = 0; o < NOPS; o++) {
-    for (int i = threadIdx.x; i < nt; i += kBitsThreads) tab[o][i] = (uint32_t)(deposit(d.op[o].lo, (uint64_t)i) >> 5);
+    // offsets in 16-byte units: every operand offset is a multiple of 128 entries
+    for (int i = threadIdx.x; i < nt; i += kBitsThreads) tab[o][i] = (uint32_t)(deposit(d.op[o].lo, (uint64_t)i) >> 7);
     if (threadIdx.x < KK) {
       int64_t a = 0;
       for (int q = 0; q < KB; q++)
         if (threadIdx.x >> q & 1) a += d.op[o].ks[q];
-      kw[o][threadIdx.x] = (uint32_t)(a >> 5);
+      kw[o][threadIdx.x] = (uint32_t)(a >> 7);
     }
     runs_to_smem(d.op[o].hi, runs[o]);
   }
@@ -339,9 +333,9 @@ k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ Bits
 #pragma unroll
   for (int o = 0; o < NOPS; o++) off[o] = tile < n_tiles ? deposit_warp(runs[o], (uint64_t)tile) : 0;
   while (tile < n_tiles) {
-    uint32_t base[NOPS];  // word offset of this tile inside each operand (operands hold < 2^37 entries)
+    const uint4* base[NOPS];
 #pragma unroll
-    for (int o = 0; o < NOPS; o++) base[o] = (uint32_t)((ptrs.bitoff[o] + off[o]) >> 5);
+    for (int o = 0; o < NOPS; o++) base[o] = (const uint4*)ptrs.p[o] + ((ptrs.bitoff[o] + off[o]) >> 7);
     uint4* outp = out + (tile << d.tile_bits);
     const int64_t next = tile + gridDim.x;
     if (next < n_tiles) {
@@ -351,36 +345,33 @@ k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ Bits
     for (int v0 = threadIdx.x; v0 < nt; v0 += kBitsThreads * G) {
       uint32_t q[G][NOPS];
       bool on[G];
-      uint32_t acc[G][4];
+      uint4 acc[G];
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const int vi = v0 + g * kBitsThreads;
         on[g] = vi < nt;
 #pragma unroll
-        for (int o = 0; o < NOPS; o++) q[g][o] = base[o] + tab[o][on[g] ? vi : 0];
-        acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0;
+        for (int o = 0; o < NOPS; o++) q[g][o] = tab[o][on[g] ? vi : 0];
+        acc[g] = make_uint4(0, 0, 0, 0);
       }
-#pragma unroll
+#pragma unroll KU
       for (int kk = 0; kk < KK; kk++) {
-        uint32_t X[G][NOPS][4];
+        uint4 X[G][NOPS];
 #pragma unroll
         for (int g = 0; g < G; g++)
 #pragma unroll
-          for (int o = 0; o < NOPS; o++) bits_load_words_rt(ptrs.p[o] + (q[g][o] + kw[o][kk]), d.op[o].hi2, X[g][o]);
+          for (int o = 0; o < NOPS; o++) X[g][o] = base[o][q[g][o] + kw[o][kk]];
 #pragma unroll
         for (int g = 0; g < G; g++) {
+          uint4 t = X[g][0];
 #pragma unroll
-          for (int w = 0; w < 4; w++) {
-            uint32_t t = X[g][0][w];
-#pragma unroll
-            for (int o = 1; o < NOPS; o++) t &= X[g][o][w];
-            acc[g][w] |= t;
-          }
+          for (int o = 1; o < NOPS; o++) { t.x &= X[g][o].x; t.y &= X[g][o].y; t.z &= X[g][o].z; t.w &= X[g][o].w; }
+          acc[g].x |= t.x; acc[g].y |= t.y; acc[g].z |= t.z; acc[g].w |= t.w;
         }
       }
 #pragma unroll
       for (int g = 0; g < G; g++)
-        if (on[g]) outp[v0 + g * kBitsThreads] = make_uint4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+        if (on[g]) outp[v0 + g * kBitsThreads] = acc[g];
     }
     tile = next;
   }

@@ -471,8 +471,8 @@ inline MergeArgs make_merge_desc(const BitLabels& lhs_bits, const BitLabels* rhs
   return m;
 }
 
-// Fused n-ary bit-packed merge: operands[i] / out are bit labels MSB first; every operand must hold the five
-// in-word lanes of the output (plans store small operands broadcast), at most kBitsMaxKB summed labels.
+// Fused n-ary bit-packed merge: operands[i] / out are bit labels MSB first; every operand must hold the seven
+// lowest output labels (plans store small operands broadcast), at most kBitsMaxKB summed labels.
 struct BitsNArgs {
   BitsNDesc d;
   bool ok = false;
@@ -523,8 +523,8 @@ inline BitsNArgs make_bits_n_desc(const std::vector<BitLabels>& operands, const 
         runs_add(lo ? bo.lo : bo.hi, lo ? j - 7 : j - 7 - d.tile_bits, it->second);
       }
     }
-    if ((nib & 31) != 31) return m;
-    if (operands[o].size() > 36) return m;  // word offsets are 32-bit
+    if (nib != 127) return m;               // every operand holds the seven lane bits: one 16-byte load per fetch
+    if (operands[o].size() > 38) return m;  // 16-byte-unit offsets are 32-bit
     bo.hi2 = nib >> 5;
     for (int q = 0; q < d.kbits; q++) bo.ks[q] = lp[o].count(ks[q]) ? int64_t(1) << lp[o][ks[q]] : 0;
   }

@@ -538,10 +538,11 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       op.md = m.d;
     }
     auto has_role = [&](int i) { return P.nodes[i].is_out || P.nodes[i].gathered || i == P.root; };
-    // wires of the five lowest output positions of `ow` that the operand does not hold
-    auto missing_low = [&](const std::vector<int32_t>& ow, const std::vector<int32_t>& w) {
+    // wires of the n_low lowest output positions of `ow` that the operand does not hold (5: the in-word lanes,
+    // enough for the two-operand kernels; 7: the whole 16-byte vector, what a fused step needs)
+    auto missing_low = [&](const std::vector<int32_t>& ow, const std::vector<int32_t>& w, int n_low) {
       std::vector<int32_t> add;
-      for (int q = std::max(0, (int)ow.size() - 5); q < (int)ow.size(); q++)
+      for (int q = std::max(0, (int)ow.size() - n_low); q < (int)ow.size(); q++)
         if (std::find(w.begin(), w.end(), ow[q]) == w.end()) add.push_back(ow[q]);
       return add;
     };
@@ -594,7 +595,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         for (size_t q = 0; q < nodes.size() && ok; q++) {
           for (auto w : wires[q])
             if (std::find(op.ow.begin(), op.ow.end(), w) == op.ow.end()) summed.insert(w);
-          ok = can_broadcast(nodes[q], missing_low(op.ow, wires[q]).size()) && wires[q].size() <= 36;
+          ok = can_broadcast(nodes[q], missing_low(op.ow, wires[q], 7).size()) && wires[q].size() <= 36;
         }
         if (!ok || (int)summed.size() > std::min(kFuseMaxK, (int)kBitsMaxKB)) continue;
         // fuse: the producer disappears, its operands join the consumer's launch
@@ -646,7 +647,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       POp& z = P.ops[consumer[i]];
       int zj = 0;
       for (int j = 0; j < z.n_operands(); j++) if (z.operand(j) == i) zj = j;
-      std::vector<int32_t> add = missing_low(z.ow, z.operand_wires(zj));
+      std::vector<int32_t> add = missing_low(z.ow, z.operand_wires(zj), z.xn.empty() ? 5 : 7);
       const PNode src = P.nodes[i];
       if (!can_broadcast(i, add.size())) add.clear();
       if (add.empty() && src.packed) continue;  // read as is
