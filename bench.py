@@ -11,9 +11,10 @@ one whole contraction (shared part + all 16 slices + combine); with N GPUs the 1
 into contiguous blocks, one per rank, and combined by one NCCL all-reduce (max).  Total work is
 fixed, so scaling is "strong"; the metric is the contraction time in seconds.
 
-Timed region: leaves resident in HBM, K executions bracketed by barrier + synchronize, CUDA events
-on the launching stream, max over ranks.  Every intermediate of a slice is far larger than L2
-(126 MB), so successive steps cannot hit in L2.  ``e2e`` times the same contraction through
+Timed region: leaves resident in HBM, K executions bracketed by barrier + synchronize, one pair of
+CUDA events per execution on the launching stream, max over ranks.  The inputs of a contraction are
+5 KB of leaf tensors and every intermediate is produced inside the step; the L2 is flushed before
+every timed execution anyway (the back-to-back figure is reported next to it).  ``e2e`` times the same contraction through
 ``TreeContraction.contract_from_host`` with the leaves in host memory (one H2D of the packed
 leaves and one D2H of the verdict inside the timed region).
 """
@@ -72,11 +73,17 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int) -> None:
         self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.window: tuple[float, float] | None = None   # host-clock bounds of the timed region
+
+    def wait_first_sample(self, timeout: float = 3.0) -> None:
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def start(self) -> None:
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -86,7 +93,7 @@ class ClockSampler:
     def _read(self) -> None:
         assert self.proc and self.proc.stdout
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self) -> dict:
         if not self.proc:
@@ -99,7 +106,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines, window = self.lines, "run (warm-up + timed region + e2e)"
+        if self.window:
+            # a sample is stamped when it is read: it describes the ~20 ms before that
+            inside = [x for x in self.lines if self.window[0] <= x[0] <= self.window[1] + 0.03]
+            if inside:
+                lines, window = inside, "timed region"
+        for _, ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -113,7 +126,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def hbm_peak() -> tuple[float, str]:
@@ -176,7 +189,7 @@ def run_reference(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,13 +236,14 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _native.launch_count()
+        sampler.wait_first_sample()
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    # back-to-back (no flush): K executions between one pair of events
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
@@ -237,17 +251,31 @@ def main() -> None:
         step()
     e1.record()
     sync_all()
-    ms = e0.elapsed_time(e1)
+    ms_b2b = e0.elapsed_time(e1)
+    # the reported number: L2 flushed before every timed step (a 256 MiB fill, twice the 126 MB L2, outside the
+    # events), one pair of CUDA events per step on the launching stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _native.launch_count()
+    sync_all()
+    t_begin = time.time()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    sync_all()
+    sampler.window = (t_begin, time.time())
+    ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = _native.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     verdict = bool(out.cpu().numpy().reshape(-1)[0])
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, float(launches), ms_b2b], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, launches = float(tmax[0]), int(tsum[1])
+        ms, launches, ms_b2b = float(tmax[0]), int(tsum[1]), float(tmax[2])
     ms_per_step = ms / args.steps
 
     # ---- end to end through the public API with HOST leaf buffers
@@ -268,6 +296,7 @@ def main() -> None:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel roofline: instrumented pass (CUDA events around every launch of the plan)
     roof = None
@@ -308,13 +337,15 @@ def main() -> None:
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_sample(tree, diagram, n_sample=16)
+            cpu = cpu_sample(tree, diagram, n_sample=128)
         line = {
             "metric": "random 3-SAT contraction time", "value": ms_per_step * 1e-3, "unit": "s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_slices": int(n_slices), "slices_per_rank": int(hi - lo),
-                       "verdict": "SAT" if verdict else "UNSAT", "l2": "inputs larger than L2",
+                       "verdict": "SAT" if verdict else "UNSAT",
+                       "l2": "flushed before every timed step (256 MiB fill outside the per-step CUDA events)",
+                       "ms_per_step_back_to_back_no_flush": ms_b2b / args.steps,
                        "peak_arena_bytes": int(plan.info["peak_bytes"]), "kernels_per_step": launches // max(args.steps, 1),
                        "alg_bytes_per_step": plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n_slices,
                        "alg_bytes_per_step_at_1B_per_entry": plan.info["alg_bytes_u8_shared"] + plan.info["alg_bytes_u8_per_slice"] * n_slices,

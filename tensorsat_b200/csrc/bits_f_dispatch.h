@@ -1,0 +1,53 @@
+// bits_f_dispatch.h — instantiation tables of k_merge_bits_f (one translation unit per (NOPS, KB) group,
+// see tsb_merge_bits_f*.cu): only mask tuples sorted in descending order are instantiated.
+#pragma once
+#include <utility>
+
+#include "lower.h"
+#include "k_merge_bits_f.cuh"
+
+namespace tsb {
+
+using BitsFKernel = void (*)(const BitsFDesc, const BitsNPtrs, uint4*);
+
+constexpr bool bits_f_sorted(int masks, int kb, int nops) {
+  for (int o = 0; o + 1 < nops; o++)
+    if (bits_f_mask(masks, kb, o) < bits_f_mask(masks, kb, o + 1)) return false;
+  return true;
+}
+
+// internal linkage: a static local of an inline function would be a process-wide unique symbol, shared with any
+// other build of these sources loaded into the same process (the test suite loads the emulated build too)
+namespace {
+
+template <int NOPS, int KB, int NP, int MASKS>
+constexpr BitsFKernel bits_f_entry() {
+  if constexpr (bits_f_sorted(MASKS, KB, NOPS)) return k_merge_bits_f<NOPS, KB, MASKS, NP>;
+  else return nullptr;
+}
+
+template <int NOPS, int KB, int NP, int... I>
+inline BitsFKernel bits_f_lookup(int masks, std::integer_sequence<int, I...>) {
+  static const BitsFKernel table[] = {bits_f_entry<NOPS, KB, NP, I>()...};
+  return table[masks];
+}
+
+template <int NOPS, int KB>
+inline BitsFKernel bits_f_kernel(int masks, int n_pair) {
+  constexpr int N = 1 << (KB * NOPS);
+  auto seq = std::make_integer_sequence<int, N>{};
+  switch (n_pair) {
+    case 0: return bits_f_lookup<NOPS, KB, 0>(masks, seq);
+    case 1: return bits_f_lookup<NOPS, KB, 1>(masks, seq);
+    default: return bits_f_lookup<NOPS, KB, 2>(masks, seq);
+  }
+}
+
+}  // namespace
+
+// one per translation unit
+BitsFKernel bits_f_kernel_4_2(int masks, int n_pair);
+BitsFKernel bits_f_kernel_3_2(int masks, int n_pair);
+BitsFKernel bits_f_kernel_small(int nops, int kb, int masks, int n_pair);  // everything else
+
+}  // namespace tsb

@@ -88,9 +88,8 @@ struct SmallOp {
   int8_t dl, dr, dout, clamp, has_rhs, pad0, pad1, pad2;
 };
 
-static __global__ void __launch_bounds__(kSmallThreads)
-k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
-  const SmallOp& d = ops[blockIdx.x];
+// one small op by the threads of one CTA
+TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
   const void* lhs = (const uint8_t*)ptrs[d.lhs_buf] + d.lhs_off;
   const void* rhs = d.has_rhs ? (const void*)((const uint8_t*)ptrs[d.rhs_buf] + d.rhs_off) : nullptr;
   void* out = (uint8_t*)ptrs[d.out_buf] + d.out_off;
@@ -124,6 +123,25 @@ k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
     }
     if (d.clamp) acc = acc != 0;
     store_from_i64(out, d.dout, oo, acc);
+  }
+}
+
+static __global__ void __launch_bounds__(kSmallThreads)
+k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
+  small_op_run(ops[blockIdx.x], ptrs);
+}
+
+// A run of consecutive waves that hold one or two small ops each (the vine at the tail of an elimination-order
+// tree, where every step depends on the one before): ONE launch of one wide CTA that executes the ops in order,
+// a block barrier between them (global writes of a CTA are visible to it after __syncthreads), instead of one
+// launch per wave.
+constexpr int kChainThreads = 1024;
+
+static __global__ void __launch_bounds__(kChainThreads)
+k_small_chain(const SmallOp* __restrict__ ops, int n_ops, void* const* __restrict__ ptrs) {
+  for (int i = 0; i < n_ops; i++) {
+    small_op_run(ops[i], ptrs);
+    __syncthreads();
   }
 }
 

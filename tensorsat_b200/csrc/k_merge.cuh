@@ -98,6 +98,28 @@ struct BitsNPtrs {
   uint64_t bitoff[kBitsMaxOps];
 };
 
+// descriptor of the factored fused merge (k_merge_bits_f.cuh): summed-wire masks known at compile time,
+// up to two "pair" output wires handled per thread so that operands that do not hold them are fetched once
+constexpr int kBitsFMaxKB = 2;
+constexpr int kBitsFMaxPair = 2;
+
+struct BitsFOperand {
+  BitRuns lo, hi;   // reduced vector-in-tile index / reduced tile index -> operand offset (entries)
+  uint32_t kw[4];   // offset, in 16-byte units, of summed-wire combination kk (wires the operand lacks add 0)
+  uint32_t pw[4];   // offset, in 16-byte units, of pair-wire combination g
+  int32_t kmask;    // summed wires the operand holds
+  int32_t held;     // pair wires the operand holds
+};
+
+struct BitsFDesc {
+  int32_t R, kbits, n_ops, tile_bits, n_pair, masks;
+  int32_t perm[kBitsMaxOps];  // slot -> index of the caller's operand (slots are sorted by kmask, descending)
+  int64_t n_vec;              // work items: 2^(R - 7 - n_pair)
+  BitRuns out_lo, out_hi;     // reduced index -> output vector index (the pair wires are holes)
+  uint32_t ow[4];             // output vector offset of pair-wire combination g
+  BitsFOperand op[kBitsMaxOps];
+};
+
 template <typename T> struct VecLoad;
 
 TSB_D void load_sub_u8(const uint8_t* p, int vbits, uint32_t buf[4]) {

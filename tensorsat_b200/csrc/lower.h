@@ -532,6 +532,123 @@ inline BitsNArgs make_bits_n_desc(const std::vector<BitLabels>& operands, const 
   return m;
 }
 
+// Factored fused merge (k_merge_bits_f.cuh).  Same preconditions as make_bits_n_desc with at most kBitsFMaxKB
+// summed labels; additionally sorts the operand slots by the summed labels they hold and picks up to
+// `max_pair` output labels (above the lane bits) that as few operand fetches as possible depend on.
+struct BitsFArgs {
+  BitsFDesc d;
+  bool ok = false;
+};
+
+inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair) {
+  BitsFArgs m;
+  const int R = (int)out_bits.size(), n = (int)operands.size();
+  if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
+  auto op = positions(out_bits);
+  std::vector<std::map<int64_t, int>> lp(n);
+  for (int o = 0; o < n; o++) {
+    if (has_dups(operands[o]) || operands[o].size() > 38) return m;
+    lp[o] = positions(operands[o]);
+  }
+  for (auto& kv : op) {
+    bool found = false;
+    for (int o = 0; o < n; o++) found = found || lp[o].count(kv.first);
+    if (!found) return m;
+  }
+  std::vector<int64_t> ks;
+  for (int o = 0; o < n; o++)
+    for (auto& kv : lp[o])
+      if (!op.count(kv.first) && std::find(ks.begin(), ks.end(), kv.first) == ks.end()) ks.push_back(kv.first);
+  const int KB = (int)ks.size();
+  if (KB > kBitsFMaxKB) return m;
+  // monotone order and the seven lane bits
+  for (int o = 0; o < n; o++) {
+    int last = -1, nlow = 0;
+    for (int j = 0; j < R; j++) {
+      auto it = lp[o].find(out_bits[R - 1 - j]);
+      if (it == lp[o].end()) { if (j < 7) return m; continue; }
+      if (it->second <= last) return m;
+      last = it->second;
+      if (j < 7 && it->second != nlow++) return m;
+    }
+  }
+  // slots sorted by summed-label mask, descending
+  std::vector<int> kmask(n, 0), slot(n);
+  for (int o = 0; o < n; o++) {
+    for (int q = 0; q < KB; q++) if (lp[o].count(ks[q])) kmask[o] |= 1 << q;
+    slot[o] = o;
+  }
+  std::stable_sort(slot.begin(), slot.end(), [&](int a, int b) { return kmask[a] > kmask[b]; });
+  // pair labels: output positions >= 8 (vector bit >= 1 keeps the two 16-byte stores of a lane pair in one sector)
+  const int vb = R - 7;
+  std::vector<int> pair_pos;
+  std::vector<int> loads(n);
+  for (int o = 0; o < n; o++) loads[o] = 1 << __builtin_popcount((unsigned)kmask[o]);
+  while ((int)pair_pos.size() < std::min(max_pair, kBitsFMaxPair) && vb - (int)pair_pos.size() > 8) {
+    int best = -1, best_score = 0;
+    for (int j = 8; j < R; j++) {
+      if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
+      int score = 0;
+      for (int o = 0; o < n; o++)
+        if (!lp[o].count(out_bits[R - 1 - j])) score += loads[o];
+      if (score > best_score) { best_score = score; best = j; }
+    }
+    if (best < 0) break;
+    pair_pos.push_back(best);
+    for (int o = 0; o < n; o++)
+      if (lp[o].count(out_bits[R - 1 - best])) loads[o] *= 2;
+  }
+  std::sort(pair_pos.begin(), pair_pos.end());
+  const int NP = (int)pair_pos.size();
+  BitsFDesc& d = m.d;
+  d = BitsFDesc{};
+  d.R = R; d.kbits = KB; d.n_ops = n; d.n_pair = NP;
+  const int vr = vb - NP;  // reduced vector-index bits
+  d.tile_bits = std::min(vr, std::min(kMergeTileBits, std::max(8, vr - 10)));
+  d.n_vec = int64_t(1) << vr;
+  for (int g = 0; g < 4; g++) {
+    uint32_t w = 0;
+    for (int q = 0; q < NP; q++) if (g >> q & 1) w += uint32_t(1) << (pair_pos[q] - 7);
+    d.ow[g] = w;
+  }
+  for (int s = 0; s < n; s++) {
+    const int o = slot[s];
+    BitsFOperand& bo = d.op[s];
+    d.perm[s] = o;
+    bo.kmask = kmask[o];
+    d.masks |= kmask[o] << (s * KB);
+    for (int kk = 0; kk < 4; kk++) {
+      int64_t a = 0;
+      for (int q = 0; q < KB; q++) if ((kk >> q & 1) && lp[o].count(ks[q])) a += int64_t(1) << lp[o][ks[q]];
+      bo.kw[kk] = (uint32_t)(a >> 7);
+    }
+    for (int q = 0; q < NP; q++) if (lp[o].count(out_bits[R - 1 - pair_pos[q]])) bo.held |= 1 << q;
+    for (int g = 0; g < 4; g++) {
+      int64_t a = 0;
+      for (int q = 0; q < NP; q++)
+        if ((g >> q & 1) && (bo.held >> q & 1)) a += int64_t(1) << lp[o][out_bits[R - 1 - pair_pos[q]]];
+      bo.pw[g] = (uint32_t)(a >> 7);
+    }
+  }
+  int in = 0;
+  for (int j = 7; j < R; j++) {
+    if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
+    const bool lo = in < d.tile_bits;
+    const int ii = lo ? in : in - d.tile_bits;
+    runs_add(lo ? d.out_lo : d.out_hi, ii, j - 7);
+    for (int s = 0; s < n; s++) {
+      auto it = lp[slot[s]].find(out_bits[R - 1 - j]);
+      if (it != lp[slot[s]].end()) runs_add(lo ? d.op[s].lo : d.op[s].hi, ii, it->second);
+    }
+    in++;
+  }
+  m.ok = true;
+  return m;
+}
+
+void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
+                         cudaStream_t s);
+
 void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
                          cudaStream_t s);
 

@@ -1,0 +1,42 @@
+// tsb_merge_bits_f.cu — launcher of the factored fused merge and the remaining k_merge_bits_f instantiations.
+#include "bits_f_dispatch.h"
+
+namespace tsb {
+
+BitsFKernel bits_f_kernel_small(int nops, int kb, int masks, int n_pair) {
+  switch (nops * 4 + kb) {
+    case 2 * 4 + 0: return bits_f_kernel<2, 0>(masks, n_pair);
+    case 2 * 4 + 1: return bits_f_kernel<2, 1>(masks, n_pair);
+    case 2 * 4 + 2: return bits_f_kernel<2, 2>(masks, n_pair);
+    case 3 * 4 + 0: return bits_f_kernel<3, 0>(masks, n_pair);
+    case 3 * 4 + 1: return bits_f_kernel<3, 1>(masks, n_pair);
+    case 4 * 4 + 0: return bits_f_kernel<4, 0>(masks, n_pair);
+    case 4 * 4 + 1: return bits_f_kernel<4, 1>(masks, n_pair);
+    default: return nullptr;
+  }
+}
+
+void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
+                         cudaStream_t stream) {
+  TSB_CHECK(d.n_ops >= 2 && d.n_ops <= kBitsMaxOps && d.kbits >= 0 && d.kbits <= kBitsFMaxKB && d.n_pair >= 0 &&
+                d.n_pair <= kBitsFMaxPair, TSB_ERR_INVALID, "internal: bad factored merge descriptor");
+  BitsNPtrs pp{};
+  for (int s = 0; s < d.n_ops; s++) {
+    const int i = d.perm[s];
+    TSB_CHECK(((uintptr_t)ptrs[i] & 15) == 0, TSB_ERR_INVALID, "internal: bit-packed operands must be 16-byte aligned");
+    pp.p[s] = (const uint32_t*)ptrs[i];
+    pp.bitoff[s] = bitoffs[i];
+  }
+  TSB_CHECK(((uintptr_t)o & 15) == 0, TSB_ERR_INVALID, "internal: bit-packed result must be 16-byte aligned");
+  BitsFKernel k = d.n_ops == 4 && d.kbits == 2 ? bits_f_kernel_4_2(d.masks, d.n_pair)
+                  : d.n_ops == 3 && d.kbits == 2 ? bits_f_kernel_3_2(d.masks, d.n_pair)
+                                                 : bits_f_kernel_small(d.n_ops, d.kbits, d.masks, d.n_pair);
+  TSB_CHECK(k != nullptr, TSB_ERR_INVALID, "internal: no factored merge kernel for masks %d", d.masks);
+  const int64_t n_tiles = d.n_vec >> d.tile_bits;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (d.n_pair == 2 ? 2 : 3)));
+  TSB_LAUNCH(k, dim3(grid), dim3(kBitsFThreads), 0, stream, d, pp, (uint4*)o);
+  ctx->launches++;
+  TSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace tsb

@@ -1,0 +1,6 @@
+// tsb_merge_bits_f32.cu — k_merge_bits_f instantiations: three operands, two summed wires.
+#include "bits_f_dispatch.h"
+
+namespace tsb {
+BitsFKernel bits_f_kernel_3_2(int masks, int n_pair) { return bits_f_kernel<3, 2>(masks, n_pair); }
+}  // namespace tsb

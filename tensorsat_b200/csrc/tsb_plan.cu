@@ -75,6 +75,8 @@ struct POp {
   std::vector<std::vector<int32_t>> xw;   // ... and their wires
   int n_fused = 0;                        // tree steps folded into this launch besides its own
   BitsNDesc nd{};                         // descriptor of a fused step (k_merge_bits_n)
+  BitsFDesc fd{};                         // ... or of its factored form (k_merge_bits_f), when use_f
+  bool use_f = false;
   int n_operands() const { return kind == OP_STEP ? 2 + (int)xn.size() : 1; }
   std::vector<int> all_operands() const { std::vector<int> v{lhs, rhs}; v.insert(v.end(), xn.begin(), xn.end()); return v; }
   int operand(int j) const { return j == 0 ? lhs : j == 1 ? rhs : xn[j - 2]; }
@@ -103,6 +105,7 @@ struct Launch {   // one entry of the once-only schedule
   int op = -1;          // single op, or
   int batch_begin = 0;  // [begin, end) into the small-op array
   int batch_end = 0;
+  bool chain = false;   // the small ops run in order inside one CTA (k_small_chain)
   float last_ms = 0;
 };
 
@@ -519,6 +522,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
     const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
     const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
+    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 2.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
     const int NN0 = (int)P.nodes.size();
     auto bits_desc = [&](POp& op) {
       BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
@@ -712,9 +716,14 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
             const auto& w = op.operand_wires(j);
             ol.push_back(bit_labels(w.data(), (int)w.size(), P.wext.data()));
           }
-          BitsNArgs m = make_bits_n_desc(ol, bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data()));
+          const BitLabels ob = bit_labels(op.ow.data(), (int)op.ow.size(), P.wext.data());
+          BitsNArgs m = make_bits_n_desc(ol, ob);
           TSB_CHECK(m.ok, TSB_ERR_INVALID, "internal: fused step is not a word-aligned monotone merge");
           op.nd = m.d;
+          if (kFusePair >= 0 && m.d.kbits <= kBitsFMaxKB) {
+            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair);
+            if (f.ok) { op.fd = f.d; op.use_f = true; }
+          }
           P.info.n_fused_steps += op.n_fused;
         }
         op.alg_bytes = op.alg_bytes_u8 / 8.0;
@@ -835,39 +844,57 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     if (nd.is_out) { buf = 1; off = 0; }
     else { buf = 0; off = nd.offset; }
   };
+  auto push_small = [&](int i) {
+    POp& op = P.ops[i];
+    const GenDesc& g = op.gd;
+    SmallOp so{};
+    so.n_free = g.n_free; so.n_red = g.n_red;
+    so.n_out_iter = (int32_t)g.n_out_iter; so.n_red_iter = (int32_t)g.n_red_iter;
+    for (int q = 0; q < g.n_free + g.n_red; q++) {
+      so.ext[q] = g.ext[q]; so.sl[q] = (int32_t)g.sl[q]; so.sr[q] = (int32_t)g.sr[q]; so.so[q] = (int32_t)g.so[q];
+    }
+    so.dl = (int8_t)g.dl; so.dr = (int8_t)g.dr; so.dout = (int8_t)g.dout;
+    so.clamp = (int8_t)g.clamp; so.has_rhs = (int8_t)g.has_rhs;
+    const PNode& o = P.nodes[op.out];
+    so.zero_first = op.gd_zero ? (int32_t)(o.bytes / dtype_size(o.dtype)) : 0;
+    buf_of(op.out, so.out_buf, so.out_off);
+    if (op.kind == OP_LEAF) {
+      so.lhs_buf = 2 + op.leaf; so.lhs_off = 0;
+      so.rhs_buf = 0; so.rhs_off = 0;
+    } else {
+      buf_of(op.lhs, so.lhs_buf, so.lhs_off);
+      buf_of(op.rhs, so.rhs_buf, so.rhs_off);
+    }
+    P.small_ops.push_back(so);
+  };
+  static const int chain_max = [] { const char* e = getenv("TSB_CHAIN_MAX_OPS"); return e ? atoi(e) : 2; }();  // 0: off
   auto build_schedule = [&](const std::vector<int>& ops, int n_waves, std::vector<Launch>& sched) {
+    std::vector<std::vector<int>> small(n_waves), big(n_waves);
+    for (int i : ops) (P.ops[i].small ? small : big)[P.ops[i].wave].push_back(i);
+    // a wave joins a chain when all it holds is one or two small ops (more are better off one CTA each)
+    auto chainable = [&](int w) { return big[w].empty() && !small[w].empty() && (int)small[w].size() <= chain_max; };
     for (int w = 0; w < n_waves; w++) {
+      if (chainable(w) && w + 1 < n_waves && chainable(w + 1)) {
+        Launch c;
+        c.wave = w;
+        c.chain = true;
+        c.batch_begin = (int)P.small_ops.size();
+        while (w < n_waves && chainable(w)) {
+          for (int i : small[w]) push_small(i);
+          w++;
+        }
+        w--;
+        c.batch_end = (int)P.small_ops.size();
+        sched.push_back(c);
+        continue;
+      }
       Launch batch;
       batch.wave = w;
       batch.batch_begin = (int)P.small_ops.size();
-      for (int i : ops) {
-        POp& op = P.ops[i];
-        if (op.wave != w || !op.small) continue;
-        const GenDesc& g = op.gd;
-        SmallOp so{};
-        so.n_free = g.n_free; so.n_red = g.n_red;
-        so.n_out_iter = (int32_t)g.n_out_iter; so.n_red_iter = (int32_t)g.n_red_iter;
-        for (int q = 0; q < g.n_free + g.n_red; q++) {
-          so.ext[q] = g.ext[q]; so.sl[q] = (int32_t)g.sl[q]; so.sr[q] = (int32_t)g.sr[q]; so.so[q] = (int32_t)g.so[q];
-        }
-        so.dl = (int8_t)g.dl; so.dr = (int8_t)g.dr; so.dout = (int8_t)g.dout;
-        so.clamp = (int8_t)g.clamp; so.has_rhs = (int8_t)g.has_rhs;
-        const PNode& o = P.nodes[op.out];
-        so.zero_first = op.gd_zero ? (int32_t)(o.bytes / dtype_size(o.dtype)) : 0;
-        buf_of(op.out, so.out_buf, so.out_off);
-        if (op.kind == OP_LEAF) {
-          so.lhs_buf = 2 + op.leaf; so.lhs_off = 0;
-          so.rhs_buf = 0; so.rhs_off = 0;
-        } else {
-          buf_of(op.lhs, so.lhs_buf, so.lhs_off);
-          buf_of(op.rhs, so.rhs_buf, so.rhs_off);
-        }
-        P.small_ops.push_back(so);
-      }
+      for (int i : small[w]) push_small(i);
       batch.batch_end = (int)P.small_ops.size();
       if (batch.batch_end > batch.batch_begin) sched.push_back(batch);
-      for (int i : ops) {
-        if (P.ops[i].wave != w || P.ops[i].small) continue;
+      for (int i : big[w]) {
         Launch l;
         l.wave = w;
         l.op = i;
@@ -961,7 +988,8 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
       ptrs[j] = base + x.offset;
       offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : 0;
     }
-    launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
+    if (op.use_f) launch_merge_bits_f(ctx, op.fd, ptrs, offs, base + o.offset, stream);
+    else launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
     return;
   }
   if (op.use_bits) {
@@ -1051,6 +1079,16 @@ int tsb_plan_info(const tsb_plan* plan, tsb_plan_info_t* info) {
   return TSB_OK;
 }
 
+// operand fetches (16 bytes each) per four output vectors of a fused step
+static int fetches_x4(const POp& op) {
+  if (op.xn.empty()) return 0;
+  if (!op.use_f) return 4 * op.nd.n_ops << op.nd.kbits;
+  int n = 0;
+  for (int s = 0; s < op.fd.n_ops; s++)
+    n += (4 >> op.fd.n_pair) << (__builtin_popcount((unsigned)op.fd.op[s].kmask) + __builtin_popcount((unsigned)op.fd.op[s].held));
+  return n;
+}
+
 int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* needed) {
   if (!plan || !needed) { tsb::set_error("null argument"); return TSB_ERR_INVALID; }
   std::ostringstream os;
@@ -1063,7 +1101,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {
@@ -1072,6 +1110,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
         os << "]";
       };
       arr("lw", op.lw); arr("rw", op.rw); arr("ow", op.ow);
+      for (size_t x = 0; x < op.xw.size(); x++) arr(x == 0 ? "xw0" : x == 1 ? "xw1" : "xw2", op.xw[x]);
     }
     os << "}";
   }
@@ -1082,7 +1121,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
   for (auto& l : all) {
     if (!first) os << ",";
     first = false;
-    os << "{\"wave\":" << l.wave << ",\"op\":" << l.op << ",\"n_small\":" << (l.batch_end - l.batch_begin)
+    os << "{\"wave\":" << l.wave << ",\"op\":" << l.op << ",\"n_small\":" << (l.batch_end - l.batch_begin) << ",\"chain\":" << (l.chain ? 1 : 0)
        << ",\"ms\":" << l.last_ms << "}";
   }
   os << "]}";
@@ -1163,8 +1202,12 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
         }
         if (l.op < 0) {
           const int n = l.batch_end - l.batch_begin;
-          TSB_LAUNCH(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
-                     (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
+          if (l.chain)
+            TSB_LAUNCH(k_small_chain, dim3(1), dim3(kChainThreads), 0, stream,
+                       (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
+          else
+            TSB_LAUNCH(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
+                       (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
           ctx->launches++;
           TSB_CUDA(cudaGetLastError());
         } else {

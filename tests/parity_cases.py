@@ -448,10 +448,11 @@ def test_bit_packed_plans_give_the_same_solution_tensors(monkeypatch, k, n, m, s
         assert bool(a) == bool(want.any())
 
 
-@pytest.mark.parametrize("n,m,seed,batch,n_out,fuse_k", [
-    (22, 90, 6, 13, 6, 2), (22, 92, 2, 11, 9, 2), (24, 100, 6, 15, 5, 2), (24, 96, 4, 12, 7, 2),
-    (22, 90, 6, 13, 6, 3), (22, 92, 2, 11, 9, 3), (22, 92, 2, 11, 9, -1)])
-def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out, fuse_k):
+@pytest.mark.parametrize("n,m,seed,batch,n_out,fuse_k,pair", [
+    (22, 90, 6, 13, 6, 2, 2), (22, 92, 2, 11, 9, 2, 2), (24, 100, 6, 15, 5, 2, 2), (24, 96, 4, 12, 7, 2, 2),
+    (22, 90, 6, 13, 6, 3, 2), (22, 92, 2, 11, 9, 3, 2), (22, 92, 2, 11, 9, -1, 2),
+    (22, 90, 6, 13, 6, 2, 1), (22, 92, 2, 11, 9, 2, 0), (24, 100, 6, 15, 5, 1, 1), (24, 96, 4, 12, 7, 2, -1)])
+def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out, fuse_k, pair):
     """Marginals over a few variables (2^n_out entries, zeros and ones) through sliced plans whose pre, per-slice,
     gathered and post steps all run bit-packed, with broadcast twins: equal to brute force, to the byte plan, and a
     partial slice range plus its complement OR to the full answer."""
@@ -462,6 +463,7 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
     monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
     monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")       # fuse consecutive packed steps whatever their size ...
     monkeypatch.setenv("TSB_FUSE_MAX_K", str(fuse_k))  # ... up to this many summed wires per launch (-1: never)
+    monkeypatch.setenv("TSB_FUSE_PAIR", str(pair))     # pair wires of k_merge_bits_f (-1: k_merge_bits_n only)
     cnf = CNFInstance.random(3, n, m, rng=seed)
     flat, net0 = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
     outs = tuple(int(v) for v in np.linspace(0, n - 1, n_out).astype(int))
@@ -479,6 +481,9 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
                             batch_log2=batch, flags=flags)
         assert (plan.info["n_packed_steps"] > 0) == (flags == 0)
         assert (plan.info["n_fused_steps"] > 0) == (flags == 0 and fuse_k >= 0)
+        if flags == 0 and 0 <= fuse_k <= 2:   # the factored kernel takes every fused step with <= 2 summed wires
+            fused = [o for o in plan.describe()["ops"] if o["fused"] > 0]
+            assert fused and all(o["factored"] == (pair >= 0) for o in fused)
         res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
         plan.execute(leaves, res)
         got[flags] = res.cpu().numpy().reshape(want.shape).copy()
