@@ -36,11 +36,7 @@ template <int NOPS, int KB>
 inline BitsFKernel bits_f_kernel(int masks, int n_pair) {
   constexpr int N = 1 << (KB * NOPS);
   auto seq = std::make_integer_sequence<int, N>{};
-  switch (n_pair) {
-    case 0: return bits_f_lookup<NOPS, KB, 0>(masks, seq);
-    case 1: return bits_f_lookup<NOPS, KB, 1>(masks, seq);
-    default: return bits_f_lookup<NOPS, KB, 2>(masks, seq);
-  }
+  return n_pair == 0 ? bits_f_lookup<NOPS, KB, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 1>(masks, seq);
 }
 
 }  // namespace

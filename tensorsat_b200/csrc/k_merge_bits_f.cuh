@@ -8,10 +8,9 @@
 //   * which summed wires an operand holds is a template parameter (MASKS, KB bits per operand slot, slots
 //     sorted by mask so that only the sorted tuples are instantiated): an operand that lacks a summed wire is
 //     fetched once for both of its values instead of once per combination;
-//   * one thread produces 2^NP output vectors that differ in NP "pair" wires chosen by the plan among the
-//     output wires that most operands do NOT hold: such an operand is fetched once for all of them (which
-//     pair wires an operand holds is uniform per launch and operand: a switch, no divergence).
-// The last operand's AND is folded into the OR over the summed-wire combinations.
+//   * optionally (NP = 1) one thread produces two output vectors that differ in a "pair" wire chosen by the
+//     plan among the output wires that most operand fetches do NOT depend on: such an operand is fetched once
+//     for both.
 #pragma once
 #include "k_merge.cuh"
 
@@ -21,63 +20,33 @@ constexpr int kBitsFThreads = 256;
 
 TSB_HD constexpr int bits_f_mask(int masks, int kb, int o) { return (masks >> (o * kb)) & ((1 << kb) - 1); }
 
-// one operand: fetch the distinct vectors (summed-wire subsets of M x pair subsets of H) and fold them in
-template <int KB, int NP, int M, int H, bool FIRST, bool LAST>
-TSB_D void bits_f_fold(const uint4* __restrict__ q, const BitsFOperand& op, uint4 (&prod)[1 << NP][1 << KB],
-                       uint4 (&acc)[1 << NP]) {
-  constexpr int KK = 1 << KB, GG = 1 << NP;
+// acc = OR over the summed-wire combinations of AND over the operands; x[o][s] holds operand o at the
+// combination s of the summed wires IT holds (s subset of its mask), so combination kk reads x[o][kk & mask_o]
+template <int NOPS, int KB, int MASKS>
+TSB_D uint4 bits_f_combine(const uint4 (&x)[NOPS][1 << KB]) {
+  constexpr int KK = 1 << KB;
+  uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int s = 0; s < KK; s++) {
-    if ((s & ~M) != 0) continue;
-    uint4 x[GG];
+  for (int kk = 0; kk < KK; kk++) {
+    uint4 t = x[0][kk & bits_f_mask(MASKS, KB, 0)];
 #pragma unroll
-    for (int g = 0; g < GG; g++)
-      if ((g & ~H) == 0) x[g] = q[op.kw[s] + op.pw[g]];
-#pragma unroll
-    for (int g = 0; g < GG; g++) {
-      const uint4 v = x[g & H];
-#pragma unroll
-      for (int kk = 0; kk < KK; kk++) {
-        if ((kk & M) != s) continue;
-        if constexpr (LAST) {
-          if constexpr (FIRST) {
-            acc[g].x |= v.x; acc[g].y |= v.y; acc[g].z |= v.z; acc[g].w |= v.w;
-          } else {
-            acc[g].x |= prod[g][kk].x & v.x; acc[g].y |= prod[g][kk].y & v.y;
-            acc[g].z |= prod[g][kk].z & v.z; acc[g].w |= prod[g][kk].w & v.w;
-          }
-        } else if constexpr (FIRST) {
-          prod[g][kk] = v;
-        } else {
-          prod[g][kk].x &= v.x; prod[g][kk].y &= v.y; prod[g][kk].z &= v.z; prod[g][kk].w &= v.w;
-        }
-      }
+    for (int o = 1; o < NOPS; o++) {
+      const uint4 v = x[o][kk & bits_f_mask(MASKS, KB, o)];
+      t.x &= v.x; t.y &= v.y; t.z &= v.z; t.w &= v.w;
     }
+    acc.x |= t.x; acc.y |= t.y; acc.z |= t.z; acc.w |= t.w;
   }
+  return acc;
 }
 
-template <int KB, int NP, int M, bool FIRST, bool LAST>
-TSB_D void bits_f_operand(const uint4* __restrict__ q, const BitsFOperand& op, uint4 (&prod)[1 << NP][1 << KB],
-                          uint4 (&acc)[1 << NP]) {
-  if constexpr (NP == 0) {
-    bits_f_fold<KB, NP, M, 0, FIRST, LAST>(q, op, prod, acc);
-  } else if constexpr (NP == 1) {
-    if (op.held) bits_f_fold<KB, NP, M, 1, FIRST, LAST>(q, op, prod, acc);
-    else bits_f_fold<KB, NP, M, 0, FIRST, LAST>(q, op, prod, acc);
-  } else {
-    switch (op.held) {
-      case 0: bits_f_fold<KB, NP, M, 0, FIRST, LAST>(q, op, prod, acc); break;
-      case 1: bits_f_fold<KB, NP, M, 1, FIRST, LAST>(q, op, prod, acc); break;
-      case 2: bits_f_fold<KB, NP, M, 2, FIRST, LAST>(q, op, prod, acc); break;
-      default: bits_f_fold<KB, NP, M, 3, FIRST, LAST>(q, op, prod, acc); break;
-    }
-  }
-}
-
+// NP = 0: one output vector per thread and iteration.  NP = 1: two vectors that differ in the plan-chosen pair
+// wire; an operand that does not hold it (uniform per launch) is fetched once for both: its second fetch is
+// predicated off and the first one's registers are copied instead.  Straight-line code either way, so every
+// fetch of an iteration is in flight before the first use.
 template <int NOPS, int KB, int MASKS, int NP>
-__global__ void __launch_bounds__(kBitsFThreads, NP == 2 ? 2 : 3)
+__global__ void __launch_bounds__(kBitsFThreads, NP == 0 ? 3 : 2)
 k_merge_bits_f(const __grid_constant__ BitsFDesc d, const __grid_constant__ BitsNPtrs ptrs, uint4* __restrict__ out) {
-  constexpr int KK = 1 << KB, GG = 1 << NP;
+  constexpr int KK = 1 << KB;
   __shared__ uint32_t tab[NOPS + 1][1 << kMergeTileBits];
   __shared__ RunsSmem runs[NOPS + 1];
   const int nt = 1 << d.tile_bits;
@@ -106,19 +75,40 @@ k_merge_bits_f(const __grid_constant__ BitsFDesc d, const __grid_constant__ Bits
       for (int o = 0; o <= NOPS; o++) off[o] = deposit_warp(runs[o], (uint64_t)next);
     }
     for (int vi = threadIdx.x; vi < nt; vi += kBitsFThreads) {
-      uint4 prod[GG][KK], acc[GG];
+      uint4 x0[NOPS][KK];
 #pragma unroll
-      for (int g = 0; g < GG; g++) acc[g] = make_uint4(0, 0, 0, 0);
-      bits_f_operand<KB, NP, bits_f_mask(MASKS, KB, 0), true, NOPS == 1>(base[0] + tab[0][vi], d.op[0], prod, acc);
-      if constexpr (NOPS > 1)
-        bits_f_operand<KB, NP, bits_f_mask(MASKS, KB, 1), false, NOPS == 2>(base[1] + tab[1][vi], d.op[1], prod, acc);
-      if constexpr (NOPS > 2)
-        bits_f_operand<KB, NP, bits_f_mask(MASKS, KB, 2), false, NOPS == 3>(base[2] + tab[2][vi], d.op[2], prod, acc);
-      if constexpr (NOPS > 3)
-        bits_f_operand<KB, NP, bits_f_mask(MASKS, KB, 3), false, NOPS == 4>(base[3] + tab[3][vi], d.op[3], prod, acc);
-      uint4* o = outp + tab[NOPS][vi];
+      for (int o = 0; o < NOPS; o++) {
+        const uint4* q = base[o] + tab[o][vi];
 #pragma unroll
-      for (int g = 0; g < GG; g++) o[d.ow[g]] = acc[g];
+        for (int s = 0; s < KK; s++)
+          if ((s & ~bits_f_mask(MASKS, KB, o)) == 0) x0[o][s] = q[d.op[o].kw[s]];
+      }
+      uint4* po = outp + tab[NOPS][vi];
+      if constexpr (NP == 1) {
+        // the second vector's real fetches are issued before anything waits on the first vector's data
+        uint4 x1[NOPS][KK];
+#pragma unroll
+        for (int o = 0; o < NOPS; o++) {
+          const uint4* q = base[o] + tab[o][vi] + d.op[o].pw[1];
+          if (d.op[o].held != 0) {
+#pragma unroll
+            for (int s = 0; s < KK; s++)
+              if ((s & ~bits_f_mask(MASKS, KB, o)) == 0) x1[o][s] = q[d.op[o].kw[s]];
+          }
+        }
+        po[0] = bits_f_combine<NOPS, KB, MASKS>(x0);
+#pragma unroll
+        for (int o = 0; o < NOPS; o++) {
+          if (d.op[o].held == 0) {
+#pragma unroll
+            for (int s = 0; s < KK; s++)
+              if ((s & ~bits_f_mask(MASKS, KB, o)) == 0) x1[o][s] = x0[o][s];
+          }
+        }
+        po[d.ow[1]] = bits_f_combine<NOPS, KB, MASKS>(x1);
+      } else {
+        po[0] = bits_f_combine<NOPS, KB, MASKS>(x0);
+      }
     }
     tile = next;
   }

@@ -325,7 +325,9 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
   };
 
   // ---- nodes ---------------------------------------------------------------------------------
-  const int batch_log2 = D.batch_log2 >= 0 ? D.batch_log2 : 24;
+  // once-only ("pre" / "post") limit: 16 MiB per tensor with all slices kept, in either representation
+  const bool will_pack = P.mode == TSB_SAT && !(P.flags & (TSB_PLAN_FORCE_GENERIC | TSB_PLAN_NO_PACK));
+  const int batch_log2 = D.batch_log2 >= 0 ? D.batch_log2 : (will_pack ? 27 : 24);
   P.nodes.resize(2 * L - 1);
   const bool sliced_any = !P.sliced.empty();
   for (int i = 0; i < 2 * L - 1; i++) {
@@ -522,7 +524,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
     const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
     const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
-    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 2.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
+    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 0.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
     const int NN0 = (int)P.nodes.size();
     auto bits_desc = [&](POp& op) {
       BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
