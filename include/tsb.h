@@ -192,7 +192,7 @@ typedef struct {
   int32_t log2_max_tensor;    /* elements, largest intermediate of one slice */
   int32_t may_overflow;       /* counting bound exceeds int64 */
   double alg_bytes_u8_shared;    /* the same steps at one byte per boolean entry (SURVEY.md §8d's definition); */
-  double alg_bytes_u8_per_slice; /* alg_bytes_* count the representation the plan uses (1/8 byte when bit-packed) */
+  double alg_bytes_u8_per_slice; /* alg_bytes_* count what the plan's launches move (1/8 byte per entry when bit-packed, no intermediates of fused steps) */
   int32_t n_packed_steps;     /* steps executed on bit-packed operands */
   int32_t n_conversions;      /* byte <-> bit conversion launches (per execution of every op once) */
   int32_t n_fused_steps;      /* tree steps folded into the launch of their consumer (their result is never stored) */

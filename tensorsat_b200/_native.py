@@ -364,7 +364,10 @@ class Plan:
         """Same, on raw device addresses (leaves packed in one staging buffer)."""
         if len(leaf_ptrs) != self.n_leaves:
             raise ValueError(f"Expected {self.n_leaves} leaf tensors, got {len(leaf_ptrs)}.")
-        arr = (C.c_void_p * max(1, len(leaf_ptrs)))(*[int(p) for p in leaf_ptrs])
+        if isinstance(leaf_ptrs, C.Array):   # a pointer table the caller keeps across calls
+            arr = leaf_ptrs
+        else:
+            arr = (C.c_void_p * max(1, len(leaf_ptrs)))(*[int(p) for p in leaf_ptrs])
         _check(lib().tsb_plan_execute(self._h, arr, C.c_int64(int(slice_begin)), C.c_int64(int(slice_end)),
                                       C.c_void_p(int(out_ptr)), stream()))
 

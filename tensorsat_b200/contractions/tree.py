@@ -158,28 +158,41 @@ class TreeContraction(Contraction):
         plan = self.plan()
         if len(leaves) != plan.n_leaves:
             raise ValueError(f"Expected {plan.n_leaves} leaf arrays, got {len(leaves)}.")
-        packed = np.concatenate([np.asarray(a, dtype=np.uint8).reshape(-1) for a in leaves])
         st = getattr(self, "_staging", None)
-        if st is None or st[0].numel() != packed.size:
-            pin = torch.empty(packed.size, dtype=torch.uint8)
+        if st is None:
+            sizes = [int(np.asarray(a).size) for a in leaves]
+            total = int(sum(sizes))
+            pin = torch.empty(total, dtype=torch.uint8)
             if _native._device == "cuda":
                 pin = pin.pin_memory()
-            dev = torch.empty(packed.size, dtype=torch.uint8, device=_native.device())
+            dev = torch.empty(total, dtype=torch.uint8, device=_native.device())
             res = torch.empty(plan.info["out_numel"], dtype=torch.uint8 if self.mode == 0 else torch.int64)
             if _native._device == "cuda":
                 res = res.pin_memory()
-            st = self._staging = (pin, dev, res)
-        pin, dev, res = st
-        pin.numpy()[:] = packed
+            offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            import ctypes
+
+            ptrs = (ctypes.c_void_p * len(leaves))(*[dev.data_ptr() + int(o) for o in offs])
+            st = self._staging = (pin, dev, res, sizes, ptrs)
+        pin, dev, res, sizes, ptrs = st
+        # one pass over the leaves: C-order bytes of every array, joined (uint8 / bool arrays are taken as they
+        # are; anything else, or a leaf of another size, shows as a length mismatch and takes the checked path)
+        try:
+            blob = b"".join([a.tobytes() for a in leaves])
+        except AttributeError:   # not numpy arrays
+            blob = b""
+        if len(blob) != pin.numel():
+            if [int(np.asarray(a).size) for a in leaves] != sizes:
+                raise ValueError("Leaf sizes differ from those of the first call.")
+            blob = np.concatenate([np.asarray(a, dtype=np.uint8).reshape(-1) for a in leaves]).tobytes()
+        pin.numpy()[:] = np.frombuffer(blob, dtype=np.uint8)
         dev.copy_(pin, non_blocking=True)
-        base = dev.data_ptr()
-        offs = np.concatenate([[0], np.cumsum([np.asarray(a).size for a in leaves])[:-1]])
         out = _native.empty(plan.info["out_numel"], self.mode)
         lo, hi = (0, plan.info["n_slices"]) if slice_range is None else slice_range
-        plan.execute_ptrs([base + int(o) for o in offs], out.data_ptr(), lo, hi)
+        plan.execute_ptrs(ptrs, out.data_ptr(), lo, hi)
         res.copy_(out, non_blocking=False)
         dims = tuple(self.wiring.wire_dims[w] for w in self.wiring.out_wires)
-        self.h2d_bytes, self.d2h_bytes = int(packed.size), int(res.numel() * res.element_size())
+        self.h2d_bytes, self.d2h_bytes = int(pin.numel()), int(res.numel() * res.element_size())
         return res.numpy().reshape(dims).copy()
 
     def contract(self, diagram: Diagram, *, slice_range: tuple[int, int] | None = None, **_ignored: Any) -> Box:

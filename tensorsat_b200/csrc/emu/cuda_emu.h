@@ -260,11 +260,45 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent
 #define TSB_DYN_SMEM(name) unsigned char* name = emu::S().dyn_smem
 #define TSB_LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
+#define TSB_LAUNCH_PDL TSB_LAUNCH
+#define TSB_PDL_TRIGGER() ((void)0)
+#define TSB_PDL_WAIT() ((void)0)
 
 #else  // real CUDA
 
 #define TSB_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define TSB_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with TSB_LAUNCH_PDL may start while the kernel
+// before it in the stream is still draining.  Such a kernel builds its shared-memory tables from its
+// parameters, then TSB_PDL_WAIT()s (griddepcontrol.wait: the preceding grid has completed and its writes are
+// visible) before it reads or writes global memory; TSB_PDL_TRIGGER() at its top lets its own successor do the
+// same.  Kernels launched with plain TSB_LAUNCH keep full stream order on both sides.  TSB_PDL=0 disables it.
+#define TSB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define TSB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+namespace tsb {
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("TSB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+}  // namespace tsb
+#define TSB_LAUNCH_PDL(kern, grid, block, smem, stream, ...) \
+  ::tsb::launch_pdl(kern, (grid), (block), (smem), (cudaStream_t)(stream), __VA_ARGS__)
 
 #endif

@@ -39,6 +39,8 @@ TSB_HD void store_from_i64(void* p, int dt, int64_t idx, int64_t v) {
 static __global__ void __launch_bounds__(256)
 k_generic(const __grid_constant__ GenDesc d, const void* __restrict__ lhs,
           const void* __restrict__ rhs, void* __restrict__ out) {
+  TSB_PDL_TRIGGER();
+  TSB_PDL_WAIT();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < d.n_out_iter; it += stride) {
     int64_t ol = 0, orr = 0, oo = 0, rem = it;
@@ -128,6 +130,8 @@ TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
 
 static __global__ void __launch_bounds__(kSmallThreads)
 k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
+  TSB_PDL_TRIGGER();
+  TSB_PDL_WAIT();
   small_op_run(ops[blockIdx.x], ptrs);
 }
 
@@ -139,6 +143,8 @@ constexpr int kChainThreads = 1024;
 
 static __global__ void __launch_bounds__(kChainThreads)
 k_small_chain(const SmallOp* __restrict__ ops, int n_ops, void* const* __restrict__ ptrs) {
+  TSB_PDL_TRIGGER();
+  TSB_PDL_WAIT();
   for (int i = 0; i < n_ops; i++) {
     small_op_run(ops[i], ptrs);
     __syncthreads();

@@ -112,6 +112,7 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
   __shared__ int64_t kL[256], kR[256];
   __shared__ uint32_t lutL[512], lutR[512], posL[32], posR[32];
   __shared__ RunsSmem runsL, runsR;
+  TSB_PDL_TRIGGER();
   const int nt = 1 << d.tile_bits;
   for (int i = threadIdx.x; i < nt; i += kBitsThreads) {
     tabL[i] = (uint32_t)deposit(d.loL, (uint64_t)i);
@@ -129,6 +130,7 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
   runs_to_smem(d.hiL, runsL);
   runs_to_smem(d.hiR, runsR);
   __syncthreads();
+  TSB_PDL_WAIT();
   const BitsLane lnL = bits_lane(d.nibL), lnR = bits_lane(d.nibR);
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const bool acc_out = d.accumulate != 0, has_rhs = d.has_rhs != 0;
@@ -241,6 +243,7 @@ k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__
   constexpr int G = KB == 0 ? 4 : 2;  // eight operand fetches in flight per thread either way
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
   __shared__ RunsSmem runsL, runsR;
+  TSB_PDL_TRIGGER();
   const int nt = 1 << d.tile_bits;
   for (int i = threadIdx.x; i < nt; i += kBitsThreads) {
     tabL[i] = (uint32_t)(deposit(d.loL, (uint64_t)i) >> 5);
@@ -249,6 +252,7 @@ k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__
   runs_to_smem(d.hiL, runsL);
   runs_to_smem(d.hiR, runsR);
   __syncthreads();
+  TSB_PDL_WAIT();
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const bool acc_out = d.accumulate != 0;
   const uint64_t kwL = KB ? (uint64_t)d.ksL[0] >> 5 : 0, kwR = KB ? (uint64_t)d.ksR[0] >> 5 : 0;
@@ -313,6 +317,7 @@ k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ Bits
   __shared__ uint32_t tab[NOPS][1 << kMergeTileBits];
   __shared__ uint32_t kw[NOPS][KK];
   __shared__ RunsSmem runs[NOPS];
+  TSB_PDL_TRIGGER();
   const int nt = 1 << d.tile_bits;
 #pragma unroll
   for (int o = 0; o < NOPS; o++) {
@@ -327,6 +332,7 @@ k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ Bits
     runs_to_smem(d.op[o].hi, runs[o]);
   }
   __syncthreads();
+  TSB_PDL_WAIT();
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   int64_t tile = blockIdx.x;
   uint64_t off[NOPS];
@@ -385,6 +391,8 @@ TSB_D uint32_t pack4(uint32_t w) { return ((w * 0x01020408u) >> 24) & 0xfu; }
 TSB_D uint32_t unpack4(uint32_t n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; }
 
 static __global__ void k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n_entries) {
+  TSB_PDL_TRIGGER();
+  TSB_PDL_WAIT();
   const int64_t n_words = (n_entries + 31) >> 5;
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = w << 5;
@@ -405,8 +413,10 @@ template <bool SRC_PACKED>
 __global__ void k_pack_map(const void* __restrict__ src, uint32_t* __restrict__ dst, int64_t n_entries,
                            const __grid_constant__ BitRuns lo, const __grid_constant__ BitRuns hi) {
   __shared__ uint32_t lane_off[32];
+  TSB_PDL_TRIGGER();
   if (threadIdx.x < 32) lane_off[threadIdx.x] = (uint32_t)deposit(lo, (uint64_t)threadIdx.x);
   __syncthreads();
+  TSB_PDL_WAIT();
   const int64_t n_words = (n_entries + 31) >> 5;
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t base = deposit(hi, (uint64_t)w);
@@ -425,6 +435,8 @@ __global__ void k_pack_map(const void* __restrict__ src, uint32_t* __restrict__ 
 
 static __global__ void k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n_entries,
                                      int accumulate) {
+  TSB_PDL_TRIGGER();
+  TSB_PDL_WAIT();
   const int64_t n_vec = (n_entries + 15) >> 4;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t h = (src[v >> 1] >> ((v & 1) * 16)) & 0xffffu;

@@ -49,6 +49,7 @@ k_merge_bits_f(const __grid_constant__ BitsFDesc d, const __grid_constant__ Bits
   constexpr int KK = 1 << KB;
   __shared__ uint32_t tab[NOPS + 1][1 << kMergeTileBits];
   __shared__ RunsSmem runs[NOPS + 1];
+  TSB_PDL_TRIGGER();
   const int nt = 1 << d.tile_bits;
 #pragma unroll
   for (int o = 0; o < NOPS; o++) {
@@ -59,6 +60,7 @@ k_merge_bits_f(const __grid_constant__ BitsFDesc d, const __grid_constant__ Bits
   for (int i = threadIdx.x; i < nt; i += kBitsFThreads) tab[NOPS][i] = (uint32_t)deposit(d.out_lo, (uint64_t)i);
   runs_to_smem(d.out_hi, runs[NOPS]);
   __syncthreads();
+  TSB_PDL_WAIT();  // tables came from the parameters; operands and result are touched from here on
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   int64_t tile = blockIdx.x;
   uint64_t off[NOPS + 1];

@@ -131,6 +131,7 @@ k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
   __shared__ int64_t kL[256], kR[256];
   __shared__ RunsSmem runsL, runsR;
+  TSB_PDL_TRIGGER();
   const MergeDesc& d = dd.m;
   const int nt = 1 << d.tile_bits;
   for (int i = threadIdx.x; i < nt; i += kSatThreads) {
@@ -147,6 +148,7 @@ k_merge_sat(const __grid_constant__ MergeSatDesc dd, const uint8_t* __restrict__
   runs_to_smem(d.hiL, runsL);
   runs_to_smem(d.hiR, runsR);
   __syncthreads();
+  TSB_PDL_WAIT();  // tables came from the parameters; operands and result are touched from here on
   const int K = 1 << d.kbits;
   const int64_t k1L = d.kbits ? d.ksL[0] : 0, k1R = d.kbits ? d.ksR[0] : 0;
   const int64_t n_tiles = d.n_vec >> d.tile_bits;

@@ -181,7 +181,7 @@ inline void launch_generic(tsb_ctx* ctx, const GenDesc& g, const void* lhs, cons
             "step with %lld outputs x %lld summed terms has no fast kernel (non-binary extents or repeated wires?)",
             (long long)g.n_out_iter, (long long)g.n_red_iter);
   const int grid = grid_for(ctx, g.n_out_iter, 256);
-  TSB_LAUNCH(k_generic, dim3(grid), dim3(256), 0, stream, g, lhs, rhs, out);
+  TSB_LAUNCH_PDL(k_generic, dim3(grid), dim3(256), 0, stream, g, lhs, rhs, out);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
 }

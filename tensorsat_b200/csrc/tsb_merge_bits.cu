@@ -8,7 +8,7 @@ template <int KB, int HL, int HR>
 static void bits_w_one(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t bl, const void* r, uint64_t br, void* o,
                        int grid, cudaStream_t stream) {
   auto k = k_merge_bits_w<KB, HL, HR>;
-  TSB_LAUNCH(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bl, (const uint32_t*)r, br, (uint4*)o);
+  TSB_LAUNCH_PDL(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bl, (const uint32_t*)r, br, (uint4*)o);
 }
 
 template <int KB, int HL>
@@ -51,13 +51,13 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
     return;
   }
   if (d.kbits == 0)
-    TSB_LAUNCH(k_merge_bits<0>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+    TSB_LAUNCH_PDL(k_merge_bits<0>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
   else if (d.kbits == 1)
-    TSB_LAUNCH(k_merge_bits<1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+    TSB_LAUNCH_PDL(k_merge_bits<1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
   else
-    TSB_LAUNCH(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
+    TSB_LAUNCH_PDL(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
@@ -66,7 +66,7 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
 template <int NOPS, int KB>
 static void bits_n_one(const BitsNDesc& d, const BitsNPtrs& pp, void* o, int grid, cudaStream_t stream) {
   auto k = k_merge_bits_n<NOPS, KB>;
-  TSB_LAUNCH(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, pp, (uint4*)o);
+  TSB_LAUNCH_PDL(k, dim3(grid), dim3(kBitsThreads), 0, stream, d, pp, (uint4*)o);
 }
 
 template <int NOPS>
@@ -103,7 +103,7 @@ void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* pt
 void launch_pack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entries, cudaStream_t stream) {
   const int64_t n_words = (n_entries + 31) >> 5;
   const int grid = (int)std::min<int64_t>((n_words + 255) / 256, (int64_t)ctx->sm_count * 16);
-  TSB_LAUNCH(k_pack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint8_t*)src, (uint32_t*)dst, n_entries);
+  TSB_LAUNCH_PDL(k_pack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint8_t*)src, (uint32_t*)dst, n_entries);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
 }
@@ -113,9 +113,9 @@ void launch_pack_map(tsb_ctx* ctx, const void* src, bool src_packed, void* dst, 
   const int64_t n_words = (n_entries + 31) >> 5;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_words + 255) / 256, (int64_t)ctx->sm_count * 16));
   if (src_packed)
-    TSB_LAUNCH(k_pack_map<true>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
+    TSB_LAUNCH_PDL(k_pack_map<true>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
   else
-    TSB_LAUNCH(k_pack_map<false>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
+    TSB_LAUNCH_PDL(k_pack_map<false>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());
 }
@@ -124,7 +124,7 @@ void launch_unpack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entr
                         cudaStream_t stream) {
   const int64_t n_vec = (n_entries + 15) >> 4;
   const int grid = (int)std::min<int64_t>((n_vec + 255) / 256, (int64_t)ctx->sm_count * 16);
-  TSB_LAUNCH(k_unpack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint32_t*)src, (uint8_t*)dst,
+  TSB_LAUNCH_PDL(k_unpack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint32_t*)src, (uint8_t*)dst,
              n_entries, accumulate ? 1 : 0);
   ctx->launches++;
   TSB_CUDA(cudaGetLastError());

@@ -76,6 +76,7 @@ struct POp {
   int n_fused = 0;                        // tree steps folded into this launch besides its own
   BitsNDesc nd{};                         // descriptor of a fused step (k_merge_bits_n)
   BitsFDesc fd{};                         // ... or of its factored form (k_merge_bits_f), when use_f
+  double launch_entries = 0;              // fused step: entries the launch must read and write (operands + result)
   bool use_f = false;
   int n_operands() const { return kind == OP_STEP ? 2 + (int)xn.size() : 1; }
   std::vector<int> all_operands() const { std::vector<int> v{lhs, rhs}; v.insert(v.end(), xn.begin(), xn.end()); return v; }
@@ -524,7 +525,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
     const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
     const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
-    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 0.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
+    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 1.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
     const int NN0 = (int)P.nodes.size();
     auto bits_desc = [&](POp& op) {
       BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
@@ -609,6 +610,8 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         op.rhs = nodes[1]; op.rw = wires[1];
         op.xn.assign(nodes.begin() + 2, nodes.end());
         op.xw.assign(wires.begin() + 2, wires.end());
+        op.launch_entries = (double)prod_ext(op.ow, P.wext);
+        for (auto& w : wires) op.launch_entries += (double)prod_ext(w, P.wext);
         op.alg_bytes += s1.alg_bytes;
         op.alg_bytes_u8 += s1.alg_bytes_u8;
         op.alg_ops += s1.alg_ops;
@@ -728,7 +731,9 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
           }
           P.info.n_fused_steps += op.n_fused;
         }
-        op.alg_bytes = op.alg_bytes_u8 / 8.0;
+        // bytes this launch must move at one bit per entry; a fused launch neither writes nor re-reads the
+        // intermediates of the steps it folds in (alg_bytes_u8 keeps SURVEY 8(d)'s per-step sum at one byte per entry)
+        op.alg_bytes = (op.launch_entries > 0 ? op.launch_entries : op.alg_bytes_u8) / 8.0;
         P.info.n_packed_steps += 1 + op.n_fused;
       }
       ops2.push_back(op);
@@ -1205,10 +1210,10 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
         if (l.op < 0) {
           const int n = l.batch_end - l.batch_begin;
           if (l.chain)
-            TSB_LAUNCH(k_small_chain, dim3(1), dim3(kChainThreads), 0, stream,
+            TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, stream,
                        (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
           else
-            TSB_LAUNCH(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
+            TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
                        (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
           ctx->launches++;
           TSB_CUDA(cudaGetLastError());

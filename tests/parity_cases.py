@@ -765,3 +765,24 @@ def test_factoring_with_the_wallace_multiplier():
         assert pairs == want and want, (nbits, N, n_out)
         cnt = TreeContraction(CudaCountRel, d.wiring, trials=2, wire_is_free=[w < 2 * nbits for w in d.wiring.wires]).contract(d)
         assert int(cnt.tensor.sum()) == len(want)
+
+
+def test_contract_from_host_matches_device_leaves():
+    """The end-to-end entry point on host buffers (what bench.py's e2e figure times): uint8 arrays take the
+    one-pass packing, wider dtypes and plain lists the checked path; both equal the device-leaf call, and the
+    staging buffers are reused across calls with different leaf values."""
+    n = 12
+    cnf = CNFInstance.random(3, n, 40, rng=5)
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    wiring = cnf.contraction_wiring()
+    c = TreeContraction(CudaFinRel, wiring, tree=find_tree_elimination(Network.from_wiring(wiring), trials=2, seed=0))
+    for spec in ("?" * n, "1" + "?" * (n - 1), "01" + "?" * (n - 2)):
+        flat = (cnf.inputs(spec) >> cnf.diagram()).flatten()
+        want = bool(brute[tuple(int(ch) for ch in spec if ch != "?")].any())
+        leaves = [b.tensor for b in flat.boxes]
+        assert bool(c.contract(flat)) == want
+        assert bool(c.contract_from_host(leaves)) == want
+        assert bool(c.contract_from_host([a.astype(np.int64) for a in leaves])) == want
+        assert bool(c.contract_from_host([a.tolist() for a in leaves])) == want
+    with pytest.raises(ValueError):
+        c.contract_from_host(leaves[:-1])
