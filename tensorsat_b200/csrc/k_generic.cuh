@@ -79,7 +79,7 @@ k_generic(const __grid_constant__ GenDesc d, const void* __restrict__ lhs,
 // addressed through a pointer table (arena base, result buffer, leaf tensors) so that the op list
 // is built once per plan.
 constexpr int kSmallMaxDims = 12;
-constexpr int kSmallThreads = 64;
+constexpr int kSmallThreads = 128;
 
 struct SmallOp {
   int32_t n_free, n_red, n_out_iter, n_red_iter;
