@@ -326,7 +326,9 @@ def main() -> None:
                     traffic = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": ("k_merge_bits" if packed else "k_merge_sat<NIBL,NIBR>") + " (per-slice launches)",
+        roof = {"bound": "hbm", "kernel": ("k_merge_bits_f<NOPS,KB,MASKS,NP> (fused bit-packed steps)" if packed else "k_merge_sat<NIBL,NIBR>") + ", per-slice launches",
+                "bytes_counted": ("operands + result of each launch at 1/8 byte per entry; intermediates of the fused steps are not stored and not counted"
+                                  if packed else "operands + result of each step at 1 byte per entry"),
                 "bytes_per_entry": 0.125 if packed else 1, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": mbytes / max(n_launch, 1), "avg_launch_ms": mms / max(n_launch, 1),

@@ -540,7 +540,8 @@ struct BitsFArgs {
   bool ok = false;
 };
 
-inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair) {
+inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
+                                  int n_top_excluded = 0) {
   BitsFArgs m;
   const int R = (int)out_bits.size(), n = (int)operands.size();
   if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
@@ -586,7 +587,7 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
   for (int o = 0; o < n; o++) loads[o] = 1 << __builtin_popcount((unsigned)kmask[o]);
   while ((int)pair_pos.size() < std::min(max_pair, kBitsFMaxPair) && vb - (int)pair_pos.size() > 8) {
     int best = -1, best_score = 0;
-    for (int j = 8; j < R; j++) {
+    for (int j = 8; j < R - n_top_excluded; j++) {  // the leading (sliced) wires stay index bits: sub-range launches
       if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
       int score = 0;
       for (int o = 0; o < n; o++)

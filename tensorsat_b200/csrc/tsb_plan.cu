@@ -116,6 +116,11 @@ using namespace tsb;
 
 struct tsb_plan {
   tsb_ctx* ctx = nullptr;
+  // slice-range restriction of the once-only ("pre") ops during one execution: the first rr_nfixed sliced wires
+  // are fixed to rr_digits (the range is an aligned power-of-two block of slice ids), see pre_block()
+  int rr_nfixed = 0;
+  std::vector<int64_t> rr_digits;
+  int rr_launches = 0;  // sub-block launches of the last execution (reported by tsb_plan_describe)
   int mode = TSB_SAT;
   uint32_t flags = 0;
   int n_leaves = 0, n_wires = 0;
@@ -726,7 +731,10 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
           TSB_CHECK(m.ok, TSB_ERR_INVALID, "internal: fused step is not a word-aligned monotone merge");
           op.nd = m.d;
           if (kFusePair >= 0 && m.d.kbits <= kBitsFMaxKB) {
-            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair);
+            int n_slab_bits = 0;
+            if (P.nodes[y].shared)
+              for (auto w : P.nodes[y].slab) n_slab_bits += ilog2(P.wext[w]);
+            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits);
             if (f.ok) { op.fd = f.d; op.use_f = true; }
           }
           P.info.n_fused_steps += op.n_fused;
@@ -962,24 +970,70 @@ int64_t shared_offset(const tsb_plan& P, const PNode& nd, const std::vector<int6
   return off * nd.reg_numel;
 }
 
+// A rank that executes an aligned block of 2^j slice ids needs, of a pre tensor that keeps sliced wires as leading
+// axes, only the sub-block where the fixed (leading) sliced wires take its values: a contiguous, aligned
+// 1 / 2^f_bits of the tensor starting at element `off`.  The fixed wires are a prefix of the node's slab.
+static void pre_block(const tsb_plan& P, const PNode& nd, int& f_bits, int64_t& off) {
+  f_bits = 0;
+  off = 0;
+  if (P.rr_nfixed == 0 || !nd.shared || nd.post || nd.gathered || nd.is_out) return;
+  for (auto w : nd.slab)
+    for (int i = 0; i < P.rr_nfixed; i++)
+      if (P.sliced[i] == w) f_bits++;
+  if (f_bits) off = shared_offset(P, nd, P.rr_digits);
+}
+
 void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vector<int64_t>* digits, bool accumulate,
               cudaStream_t stream) {
   tsb_ctx* ctx = P.ctx;
+  // pre ops of a restricted execution: output sub-block (f bits fewer) and the matching operand sub-blocks
+  int fo = 0;
+  int64_t oo = 0;
+  if (!op.per_slice && digits == nullptr) pre_block(P, P.nodes[op.out], fo, oo);
+  auto operand_off = [&](const PNode& x) {
+    int fx = 0;
+    int64_t ox = 0;
+    if (fo) pre_block(P, x, fx, ox);
+    return ox;
+  };
   if (op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND) {
     const PNode& src = P.nodes[op.lhs];
     const PNode& dst = P.nodes[op.out];
     if (op.kind != OP_UNPACK) {
-      if (op.use_bits)
-        launch_merge_bits(ctx, op.md, base + src.offset, 0, nullptr, 0, base + dst.offset, stream);
-      else if (op.cv_map)
-        launch_pack_map(ctx, base + src.offset, op.kind == OP_EXPAND, base + dst.offset, dst.stored_numel(), op.cv_lo,
-                        op.cv_hi, stream);
-      else
-        launch_pack_bits(ctx, base + src.offset, base + dst.offset, src.stored_numel(), stream);
+      const int64_t so = operand_off(src);   // entries; src and dst keep the same sliced wires
+      if (op.use_bits) {
+        MergeDesc d = op.md;
+        if (fo && (d.n_vec >> fo) >= (int64_t(1) << d.tile_bits) && (oo & 127) == 0) {
+          d.n_vec >>= fo;
+          P.rr_launches++;
+          launch_merge_bits(ctx, d, base + src.offset, (uint64_t)so, nullptr, 0, base + dst.offset + (oo >> 3), stream);
+        } else {
+          launch_merge_bits(ctx, d, base + src.offset, 0, nullptr, 0, base + dst.offset, stream);
+        }
+      } else if (op.cv_map) {
+        const bool src_packed = op.kind == OP_EXPAND;
+        const int64_t n = dst.stored_numel();
+        if (fo && (n >> fo) >= 1024 && (oo & 127) == 0 && (!src_packed || (so & 31) == 0) && ++P.rr_launches)
+          launch_pack_map(ctx, base + src.offset + (src_packed ? (so >> 3) : so), src_packed, base + dst.offset + (oo >> 3),
+                          n >> fo, op.cv_lo, op.cv_hi, stream);
+        else
+          launch_pack_map(ctx, base + src.offset, src_packed, base + dst.offset, n, op.cv_lo, op.cv_hi, stream);
+      } else {
+        const int64_t n = src.stored_numel();
+        if (fo && (n >> fo) >= 1024 && (oo & 127) == 0 && ++P.rr_launches)
+          launch_pack_bits(ctx, base + src.offset + oo, base + dst.offset + (oo >> 3), n >> fo, stream);
+        else
+          launch_pack_bits(ctx, base + src.offset, base + dst.offset, n, stream);
+      }
       return;
     }
     void* pd = dst.is_out ? out_ptr : (void*)(base + dst.offset);
     if (op.per_slice && dst.gathered) pd = (uint8_t*)pd + shared_offset(P, dst, *digits);
+    if (fo && (src.stored_numel() >> fo) >= 1024 && (oo & 127) == 0) {
+      P.rr_launches++;
+      launch_unpack_bits(ctx, base + src.offset + (oo >> 3), (uint8_t*)pd + oo, src.stored_numel() >> fo, false, stream);
+      return;
+    }
     launch_unpack_bits(ctx, base + src.offset, pd, src.stored_numel(), accumulate && dst.is_out, stream);
     return;
   }
@@ -990,13 +1044,22 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     // fused n-ary step on packed operands
     const void* ptrs[kBitsMaxOps];
     uint64_t offs[kBitsMaxOps];
+    const bool sub = fo && op.use_f && (op.fd.n_vec >> fo) >= (int64_t(1) << op.fd.tile_bits) && (oo & 127) == 0;
     for (int j = 0; j < op.n_operands(); j++) {
       const PNode& x = P.nodes[op.operand(j)];
       ptrs[j] = base + x.offset;
-      offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : 0;
+      offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : sub ? (uint64_t)operand_off(x) : 0;
     }
-    if (op.use_f) launch_merge_bits_f(ctx, op.fd, ptrs, offs, base + o.offset, stream);
-    else launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
+    if (sub) {
+      BitsFDesc d = op.fd;
+      d.n_vec >>= fo;
+      P.rr_launches++;
+      launch_merge_bits_f(ctx, d, ptrs, offs, base + o.offset + (oo >> 3), stream);
+    } else if (op.use_f) {
+      launch_merge_bits_f(ctx, op.fd, ptrs, offs, base + o.offset, stream);
+    } else {
+      launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
+    }
     return;
   }
   if (op.use_bits) {
@@ -1005,6 +1068,14 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     if (op.per_slice) {
       if (a.shared) bl = (uint64_t)shared_offset(P, a, *digits);
       if (b.shared) br = (uint64_t)shared_offset(P, b, *digits);
+    }
+    if (fo && (op.md.n_vec >> fo) >= (int64_t(1) << op.md.tile_bits) && (oo & 127) == 0) {
+      MergeDesc d = op.md;
+      d.n_vec >>= fo;
+      P.rr_launches++;
+      launch_merge_bits(ctx, d, base + a.offset, (uint64_t)operand_off(a), base + b.offset, (uint64_t)operand_off(b),
+                        base + o.offset + (oo >> 3), stream);
+      return;
     }
     launch_merge_bits(ctx, op.md, base + a.offset, bl, base + b.offset, br, base + o.offset, stream);
     return;
@@ -1034,6 +1105,17 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
   if (op.use_merge && ((uintptr_t)pl & al) == 0 && ((uintptr_t)pr & ar) == 0 && ((uintptr_t)po & 15) == 0) {
     MergeDesc d = op.md;
     d.accumulate = acc ? 1 : 0;
+    if (fo && !o.is_out && !acc && (d.n_vec >> fo) >= (int64_t(1) << d.tile_bits)) {
+      const uint8_t* ql = pl + operand_off(a) * dtype_size(a.dtype);
+      const uint8_t* qr = pr + operand_off(b) * dtype_size(b.dtype);
+      uint8_t* qo = (uint8_t*)po + oo * dtype_size(dout);
+      if (((uintptr_t)ql & al) == 0 && ((uintptr_t)qr & ar) == 0 && ((uintptr_t)qo & 15) == 0) {
+        d.n_vec >>= fo;
+        P.rr_launches++;
+        launch_merge(ctx, d, ql, a.dtype, qr, b.dtype, qo, dout, clamp, stream);
+        return;
+      }
+    }
     launch_merge(ctx, d, pl, a.dtype, pr, b.dtype, po, dout, clamp, stream);
   } else if (op.has_gd && !acc && dout == o.dtype) {
     if (op.gd_zero) TSB_CUDA(cudaMemsetAsync(po, 0, o.bytes, stream));
@@ -1099,7 +1181,8 @@ static int fetches_x4(const POp& op) {
 int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* needed) {
   if (!plan || !needed) { tsb::set_error("null argument"); return TSB_ERR_INVALID; }
   std::ostringstream os;
-  os << "{\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices << ",\"ops\":[";
+  os << "{\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices
+     << ",\"restricted_launches\":" << plan->rr_launches << ",\"ops\":[";
   bool first = true;
   for (auto& op : plan->ops) {
     if (!first) os << ",";
@@ -1237,7 +1320,22 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
         }
       }
     };
+    // A rank that executes an aligned power-of-two block of slice ids computes only its own sub-blocks of the
+    // once-only tensors that keep sliced wires (run_step / pre_block); everything else is replicated.
+    P.rr_nfixed = 0;
+    P.rr_launches = 0;
+    {
+      static const bool restrict_pre = [] { const char* e = getenv("TSB_PRE_RESTRICT"); return !(e && e[0] == '0'); }();
+      const int64_t n = slice_end - slice_begin, total = P.info.n_slices;
+      bool binary = !P.sliced.empty();
+      for (auto w : P.sliced) binary = binary && P.wext[w] == 2;
+      if (restrict_pre && binary && n > 0 && n < total && (n & (n - 1)) == 0 && slice_begin % n == 0) {
+        P.rr_nfixed = (int)P.sliced.size() - ilog2(n);
+        P.rr_digits = slice_digits(P, slice_begin);
+      }
+    }
     run_schedule(P.schedule);
+    P.rr_nfixed = 0;
     // per-slice part
     if (!P.sliced.empty()) {
       for (int64_t sid = slice_begin; sid < slice_end; sid++) {

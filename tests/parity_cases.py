@@ -786,3 +786,47 @@ def test_contract_from_host_matches_device_leaves():
         assert bool(c.contract_from_host([a.tolist() for a in leaves])) == want
     with pytest.raises(ValueError):
         c.contract_from_host(leaves[:-1])
+
+
+def test_slice_blocks_restrict_the_once_only_tensors():
+    """A rank that executes an aligned power-of-two block of slice ids computes only its own sub-blocks of the
+    once-only tensors that keep sliced wires (tsb_plan.cu: pre_block).  Plans large enough for the sub-block
+    launches to happen, both semirings: every block alone, and the blocks of a partition combined (OR / sum),
+    must give what the full range gives, and that must be brute force."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    n, m, seed = 22, 86, 11
+    cnf = CNFInstance.random(3, n, m, rng=seed)
+    flat, net0 = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
+    outs = (0, 7, 15, 21)
+    net = Network(net0.inputs, outs, net0.size_dict)
+    tree = find_tree_elimination(net, trials=2, seed=seed)
+    tree = tree.slice_to(tree.width() - 3)
+    assert tree.num_slices == 8
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    rest = tuple(v for v in range(n) if v not in outs)
+    leaves = [_native.upload(b.tensor.astype(np.uint8)) for b in flat.boxes]
+    free = [w < n for w in range(net.num_wires)]
+    for mode, want in ((_native.MODE_SAT, brute.any(axis=rest).astype(np.uint8)), (_native.MODE_COUNT, brute.sum(axis=rest, dtype=np.int64))):
+        plan = _native.Plan(net.inputs, outs, net.size_dict, tree.ssa_path, tree.sliced_wires, mode=mode, batch_log2=30,
+                            wire_is_free=free if mode == _native.MODE_COUNT else None)
+        full = _native.empty(plan.info["out_numel"], mode)
+        plan.execute(leaves, full)
+        assert plan.describe()["restricted_launches"] == 0
+        assert np.array_equal(full.cpu().numpy().reshape(want.shape), want)
+        for size in (4, 2, 1):
+            parts = []
+            for lo in range(0, 8, size):
+                r = torch.zeros_like(full)
+                plan.execute(leaves, r, lo, lo + size)
+                parts.append(r.cpu().numpy().reshape(want.shape).copy())
+            if mode == _native.MODE_SAT:
+                assert plan.describe()["restricted_launches"] > 0
+            comb = np.bitwise_or.reduce(parts) if mode == _native.MODE_SAT else np.sum(parts, axis=0)
+            assert np.array_equal(comb, want), (mode, size)
+        # an unaligned range is executed without the restriction
+        r = torch.zeros_like(full)
+        plan.execute(leaves, r, 1, 3)
+        assert plan.describe()["restricted_launches"] == 0
