@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kBitsThreads, 3)
 k_merge_bits_n(const __grid_constant__ BitsNDesc d, const __grid_constant__ BitsNPtrs ptrs, uint4* __restrict__ out) {
   constexpr int KK = 1 << KB;
   constexpr int G = 2;   // operand fetches in flight per thread: G * NOPS (times KU)
-  constexpr int KU = NOPS * KK <= 8 ? KK : (NOPS <= 2 ? 2 : 1);  // unrolling further only spills
+  [[maybe_unused]] constexpr int KU = NOPS * KK <= 8 ? KK : (NOPS <= 2 ? 2 : 1);  // unrolling further only spills
   __shared__ uint32_t tab[NOPS][1 << kMergeTileBits];
   __shared__ uint32_t kw[NOPS][KK];
   __shared__ RunsSmem runs[NOPS];

@@ -638,10 +638,16 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     std::vector<std::vector<POp>> after(NN0);  // conversions emitted right after the producer of a node
     for (int i = 0; i < NN0; i++) prod_rep[i] = cons_rep[i] = i;
     for (int i = 0; i < NN0; i++) {
-      const bool role = has_role(i);  // bytes must exist in node i
+      bool role = has_role(i);  // bytes must exist in node i
       const bool Pp = made_packed[i] != 0;
       const bool Cp = consumer[i] >= 0 && P.ops[consumer[i]].use_bits;
       if (!Pp && !Cp) continue;
+      // a gathered tensor between two packed steps stays packed: slice s fills bit block s (16-byte aligned when a
+      // block holds at least 128 entries), the tail of the tree reads it as it is
+      static const bool pack_gathered = [] { const char* e = getenv("TSB_PACK_GATHERED"); return !(e && e[0] == '0'); }();
+      if (pack_gathered && role && P.nodes[i].gathered && !P.nodes[i].is_out && i != P.root && Pp && Cp &&
+          P.nodes[i].reg_numel % 128 == 0)
+        role = false;
       const bool bytes_in_i = !Pp || role || (consumer[i] >= 0 && !Cp);
       if (Pp) {
         if (bytes_in_i) {  // the step writes a packed temporary that is unpacked into node i
@@ -1050,15 +1056,17 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
       ptrs[j] = base + x.offset;
       offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : sub ? (uint64_t)operand_off(x) : 0;
     }
+    // a packed gathered result: slice s fills bit block s
+    uint8_t* po_bits = base + o.offset + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0);
     if (sub) {
       BitsFDesc d = op.fd;
       d.n_vec >>= fo;
       P.rr_launches++;
       launch_merge_bits_f(ctx, d, ptrs, offs, base + o.offset + (oo >> 3), stream);
     } else if (op.use_f) {
-      launch_merge_bits_f(ctx, op.fd, ptrs, offs, base + o.offset, stream);
+      launch_merge_bits_f(ctx, op.fd, ptrs, offs, po_bits, stream);
     } else {
-      launch_merge_bits_n(ctx, op.nd, ptrs, offs, base + o.offset, stream);
+      launch_merge_bits_n(ctx, op.nd, ptrs, offs, po_bits, stream);
     }
     return;
   }
@@ -1077,7 +1085,8 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
                         base + o.offset + (oo >> 3), stream);
       return;
     }
-    launch_merge_bits(ctx, op.md, base + a.offset, bl, base + b.offset, br, base + o.offset, stream);
+    launch_merge_bits(ctx, op.md, base + a.offset, bl, base + b.offset, br,
+                      base + o.offset + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0), stream);
     return;
   }
   const uint8_t* pl = base + a.offset;
@@ -1191,7 +1200,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {

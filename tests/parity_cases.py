@@ -484,6 +484,8 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
         if flags == 0 and 0 <= fuse_k <= 2:   # the factored kernel takes every fused step with <= 2 summed wires
             fused = [o for o in plan.describe()["ops"] if o["fused"] > 0]
             assert fused and all(o["factored"] == (pair >= 0) for o in fused)
+        if flags == 0 and (n, m, seed) == (24, 100, 6):   # this plan gathers a per-slice result that stays bit-packed
+            assert any(o["per_slice"] and o["out_gathered"] and o["out_packed"] for o in plan.describe()["ops"])
         res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
         plan.execute(leaves, res)
         got[flags] = res.cpu().numpy().reshape(want.shape).copy()
