@@ -171,11 +171,23 @@ typedef struct {
   uint32_t flags;              /* TSB_PLAN_* */
 } tsb_plan_desc;
 
-#define TSB_PLAN_NO_GRAPH 1u     /* launch kernels directly instead of replaying a CUDA graph */
+#define TSB_PLAN_NO_GRAPH 1u     /* reserved: plans launch their kernels directly (overlap comes from programmatic
+                                    dependent launch); accepted and ignored */
 #define TSB_PLAN_FORCE_GENERIC 2u /* use only the generic kernel (parity reference on device) */
 #define TSB_PLAN_NO_GEMM 4u      /* never lower a step to the tcgen05 GEMM */
 #define TSB_PLAN_NO_PACK 8u      /* keep every boolean intermediate at one byte per entry (no bit-packing) */
 #define TSB_PLAN_NO_FUSE 16u     /* one launch per tree step (no fused n-ary steps) */
+/* Environment knobs read by the library (A/B runs and tests; defaults in parentheses):
+ *   TSB_PDL (1)              0: plain stream order instead of programmatic dependent launch
+ *   TSB_PACK_MIN_LOG2 (20)   steps touching a tensor of at least 2^x entries run bit-packed
+ *   TSB_PACK_EXPAND_LOG2 (27) largest broadcast twin of a small operand, log2 entries
+ *   TSB_PACK_GATHERED (1)    0: gathered per-slice results are stored as bytes even between packed steps
+ *   TSB_FUSE_MIN_LOG2 (22)   consecutive packed steps are fused across intermediates of at least 2^x entries
+ *   TSB_FUSE_MAX_K (2)       summed wires per fused launch (-1: never fuse)
+ *   TSB_FUSE_PAIR (1)        pair wires of k_merge_bits_f (0: none, -1: k_merge_bits_n only)
+ *   TSB_CHAIN_MAX_OPS (2)    waves of at most this many small ops join a single-CTA chain launch (0: off)
+ *   TSB_PRE_RESTRICT (1)     0: a rank computes the once-only tensors in full whatever its slice block
+ *   TSB_PERMUTE_T4 (1)       0: never use the 4x4 register-transpose permute kernel */
 
 typedef struct {
   int64_t n_slices;

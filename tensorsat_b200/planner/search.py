@@ -278,6 +278,93 @@ def _tree_from_order(net: Network, order: Sequence[int]) -> SSAPath:
     return tuple(path)
 
 
+def _anneal_order_tail(
+    net: Network, order: Sequence[int], rng: random.Random, iters: int, tail: int = 64
+) -> list[int]:
+    """Simulated annealing on the LAST ``tail`` wires of an elimination order.
+
+    Greedy min-fill / min-degree orders eliminate the cheap wires first (on a CNF network: the
+    internal wires of the clause gadgets), and all of them end within a few percent of each
+    other; what decides the cost is the order of the densely connected wires left at the end
+    (the variables).  The head of the order is eliminated once on the wire primal graph; the
+    tail is then permuted (swaps and single-wire moves) under the proxy cost
+    sum over eliminated wires of 2^(weight of the wire and its neighbours at that moment),
+    evaluated on bit sets.  Host-side, deterministic for a given seed.
+    """
+    order = list(order)
+    T = min(tail, len(order))
+    if T < 3 or iters <= 0:
+        return order
+    head, tl = order[: len(order) - T], order[len(order) - T :]
+    adj: dict[int, set[int]] = {w: set() for ws in net.inputs for w in ws}
+    for ws in net.inputs:
+        s = set(ws)
+        for w in s:
+            adj[w] |= s - {w}
+    for w in head:
+        nb = adj.pop(w)
+        for a in nb:
+            adj[a] |= nb - {a}
+            adj[a].discard(w)
+    verts = list(tl) + sorted(w for w in adj if w not in set(tl))   # tail wires first, then output wires
+    index = {w: i for i, w in enumerate(verts)}
+    lg = [math.log2(net.size_dict[w]) for w in verts]
+    uniform = all(abs(x - 1.0) < 1e-12 for x in lg)
+    adj0 = [0] * len(verts)
+    for w in verts:
+        m = 0
+        for a in adj[w]:
+            m |= 1 << index[a]
+        adj0[index[w]] = m
+    full = (1 << len(verts)) - 1
+
+    def weight(mask: int) -> float:
+        if uniform:
+            return float(bin(mask).count("1"))
+        t = 0.0
+        while mask:
+            b = mask & -mask
+            t += lg[b.bit_length() - 1]
+            mask ^= b
+        return t
+
+    def cost(perm: Sequence[int]) -> float:
+        a = adj0[:]
+        alive = full
+        tot = 0.0
+        for v in perm:
+            nb = a[v] & alive & ~(1 << v)
+            tot += 2.0 ** (weight(nb) + lg[v])
+            alive &= ~(1 << v)
+            m = nb
+            while m:
+                b = m & -m
+                a[b.bit_length() - 1] |= nb
+                m ^= b
+        return math.log2(tot)
+
+    cur = list(range(T))
+    cc = cost(cur)
+    best, bc = cur[:], cc
+    t_hi, t_lo = 0.3, 0.01
+    for it in range(iters):
+        temp = t_hi * (t_lo / t_hi) ** (it / iters)
+        i, j = rng.randrange(T), rng.randrange(T)
+        if i == j:
+            continue
+        new = cur[:]
+        if rng.random() < 0.5:
+            new[i], new[j] = new[j], new[i]
+        else:
+            new.insert(j, new.pop(i))
+        c = cost(new)
+        if c < cc or rng.random() < math.exp((cc - c) / temp):
+            cur, cc = new, c
+            if c < bc:
+                best, bc = new[:], c
+    return head + [tl[i] for i in best]
+
+
 def find_tree_elimination(
     net: Network,
     *,
@@ -285,12 +372,17 @@ def find_tree_elimination(
     seed: int = 0,
     minimize: str = "combo",
     max_log2_size: float | None = None,
+    anneal_iters: int = 0,
+    anneal_tail: int = 64,
+    anneal_restarts: int = 1,
 ) -> ContractionTree:
-    """Best of ``trials`` randomised min-fill / min-degree elimination orders."""
+    """Best of ``trials`` randomised min-fill / min-degree elimination orders; with ``anneal_iters`` > 0 the
+    best order's tail is then refined by simulated annealing (kept only if the real objective improves)."""
     if net.num_leaves == 1:
         return ContractionTree(net, ())
     rng = random.Random(seed)
     best: tuple[float, ContractionTree] | None = None
+    best_order: list[int] = []
     for t in range(max(1, trials)):
         heuristic = "min_fill" if t % 2 == 0 else "min_degree"
         noise = 0.0 if t < 2 else rng.choice([0.02, 0.05, 0.1, 0.2, 0.4])
@@ -299,5 +391,14 @@ def find_tree_elimination(
         obj = _objective(tree, minimize, max_log2_size)
         if best is None or obj < best[0]:
             best = (obj, tree)
+            best_order = order
     assert best is not None
+    for _ in range(max(1, anneal_restarts) if anneal_iters > 0 else 0):
+        # the proxy cost of the annealing tracks the real objective only loosely: every restart is judged by the
+        # real one
+        order = _anneal_order_tail(net, best_order, rng, anneal_iters, anneal_tail)
+        tree = ContractionTree(net, _tree_from_order(net, order))
+        obj = _objective(tree, minimize, max_log2_size)
+        if obj < best[0]:
+            best = (obj, tree)
     return best[1]
