@@ -87,7 +87,7 @@ struct SmallOp {
   int32_t lhs_buf, rhs_buf, out_buf;  // indices into the pointer table
   int32_t zero_first;                 // number of output elements to clear first (repeated labels)
   int64_t lhs_off, rhs_off, out_off;  // byte offsets
-  int8_t dl, dr, dout, clamp, has_rhs, pad0, pad1, pad2;
+  int8_t dl, dr, dout, clamp, has_rhs, binary /* 1: every extent is 2 */, pad1, pad2;
 };
 
 // one small op by the threads of one CTA
@@ -98,6 +98,33 @@ TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
   if (d.zero_first) {
     for (int i = threadIdx.x; i < d.zero_first; i += blockDim.x) store_from_i64(out, d.dout, i, 0);
     __syncthreads();
+  }
+  if (d.binary) {
+    // every extent is 2 (all BASELINE networks): index digits are bits, no integer division
+    for (int it = threadIdx.x; it < d.n_out_iter; it += blockDim.x) {
+      int ol = 0, orr = 0, oo = 0;
+      for (int f = d.n_free - 1, q = 0; f >= 0; f--, q++) {
+        const int i = (it >> q) & 1;
+        ol += i * d.sl[f];
+        orr += i * d.sr[f];
+        oo += i * d.so[f];
+      }
+      int64_t acc = 0;
+      for (int r = 0; r < d.n_red_iter; r++) {
+        int pl = ol, pr = orr;
+        for (int q = d.n_free + d.n_red - 1, z = 0; q >= d.n_free; q--, z++) {
+          const int i = (r >> z) & 1;
+          pl += i * d.sl[q];
+          pr += i * d.sr[q];
+        }
+        const int64_t a = load_as_i64(lhs, d.dl, pl);
+        const int64_t b = d.has_rhs ? load_as_i64(rhs, d.dr, pr) : 1;
+        acc += a * b;
+      }
+      if (d.clamp) acc = acc != 0;
+      store_from_i64(out, d.dout, oo, acc);
+    }
+    return;
   }
   for (int it = threadIdx.x; it < d.n_out_iter; it += blockDim.x) {
     int ol = 0, orr = 0, oo = 0, rem = it;

@@ -876,6 +876,8 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     }
     so.dl = (int8_t)g.dl; so.dr = (int8_t)g.dr; so.dout = (int8_t)g.dout;
     so.clamp = (int8_t)g.clamp; so.has_rhs = (int8_t)g.has_rhs;
+    so.binary = 1;
+    for (int q = 0; q < g.n_free + g.n_red; q++) if (g.ext[q] != 2) so.binary = 0;
     const PNode& o = P.nodes[op.out];
     so.zero_first = op.gd_zero ? (int32_t)(o.bytes / dtype_size(o.dtype)) : 0;
     buf_of(op.out, so.out_buf, so.out_off);
