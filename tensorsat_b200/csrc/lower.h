@@ -538,10 +538,11 @@ inline BitsNArgs make_bits_n_desc(const std::vector<BitLabels>& operands, const 
 struct BitsFArgs {
   BitsFDesc d;
   bool ok = false;
+  long wf_chosen = 0, wf_default = 0;  // modelled L1 wavefronts per work item: chosen lane wires / output bits 8..11
 };
 
 inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
-                                  int n_top_excluded = 0) {
+                                  int n_top_excluded = 0, bool choose_lanes = true) {
   BitsFArgs m;
   const int R = (int)out_bits.size(), n = (int)operands.size();
   if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
@@ -631,9 +632,64 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
       bo.pw[g] = (uint32_t)(a >> 7);
     }
   }
-  int in = 0;
-  for (int j = 7; j < R; j++) {
-    if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
+  // Which output wires index the 32 lanes of a warp.  A warp-wide 16-byte-per-lane access costs one L1 wavefront
+  // per distinct 128-byte line, and these steps are bound by exactly that.  Lane bit 0 stays the lowest vector bit
+  // (two lanes fill one 32-byte sector of the result); the other four are chosen, by exhaustive search over the
+  // eligible output wires, to minimise wavefronts per work item: an operand that does not hold a lane wire, or
+  // holds it among its own address bits 7..9, is fetched from fewer lines.
+  std::vector<int> lanes;
+  if (choose_lanes && vr >= 6) {
+    std::vector<int> cand;
+    for (int j = 8; j < R - n_top_excluded; j++)
+      if (std::find(pair_pos.begin(), pair_pos.end(), j) == pair_pos.end()) cand.push_back(j);
+    const int C = (int)cand.size();
+    if (C >= 4) {
+      // per operand and candidate: held?, and whether it lands within the operand's first 128 bytes (position <= 9)
+      std::vector<std::vector<int>> cls(n, std::vector<int>(C, 0));  // 0: not held, 1: held in-line, 2: held, new line
+      std::vector<int> fetch(n);
+      for (int o = 0; o < n; o++) {
+        fetch[o] = 1 << (__builtin_popcount((unsigned)kmask[o]));
+        for (int q = 0; q < NP; q++) if (lp[o].count(out_bits[R - 1 - pair_pos[q]])) fetch[o] *= 2;
+        for (int c = 0; c < C; c++) {
+          auto it = lp[o].find(out_bits[R - 1 - cand[c]]);
+          if (it != lp[o].end()) cls[o][c] = it->second <= 9 ? 1 : 2;
+        }
+      }
+      long best_cost = -1;
+      int bi[4] = {0, 1, 2, 3};
+      for (int a = 0; a < C; a++)
+        for (int b = a + 1; b < C; b++)
+          for (int c = b + 1; c < C; c++)
+            for (int e = c + 1; e < C; e++) {
+              const int pick[4] = {a, b, c, e};
+              // result lines per warp store: contiguous run of lane wires from output bit 7 upwards
+              int run = 1;
+              for (int q = 0; q < 4 && cand[pick[q]] == 7 + run; q++) run++;
+              long cost = (long)(1 << NP) * (run >= 3 ? 4 : run == 2 ? 8 : 16);
+              for (int o = 0; o < n; o++) {
+                int far = 0;
+                for (int q = 0; q < 4; q++) far += cls[o][pick[q]] == 2;
+                cost += (long)fetch[o] << far;
+              }
+              if (a == 0 && b == 1 && c == 2 && e == 3) m.wf_default = cost;
+              if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                for (int q = 0; q < 4; q++) bi[q] = pick[q];
+              }
+            }
+      m.wf_chosen = best_cost;
+      for (int q = 0; q < 4; q++) lanes.push_back(cand[bi[q]]);
+    }
+  }
+  std::vector<int> index_bits;  // reduced index bit -> output bit
+  index_bits.push_back(7);
+  for (int j : lanes) index_bits.push_back(j);
+  for (int j = 8; j < R; j++)
+    if (std::find(pair_pos.begin(), pair_pos.end(), j) == pair_pos.end() &&
+        std::find(lanes.begin(), lanes.end(), j) == lanes.end())
+      index_bits.push_back(j);
+  for (int in = 0; in < (int)index_bits.size(); in++) {
+    const int j = index_bits[in];
     const bool lo = in < d.tile_bits;
     const int ii = lo ? in : in - d.tile_bits;
     runs_add(lo ? d.out_lo : d.out_hi, ii, j - 7);
@@ -641,8 +697,11 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
       auto it = lp[slot[s]].find(out_bits[R - 1 - j]);
       if (it != lp[slot[s]].end()) runs_add(lo ? d.op[s].lo : d.op[s].hi, ii, it->second);
     }
-    in++;
   }
+  // deposit_warp handles one run per lane
+  if (d.out_hi.n > 32) return m;
+  for (int s = 0; s < n; s++)
+    if (d.op[s].hi.n > 32) return m;
   m.ok = true;
   return m;
 }

@@ -76,6 +76,7 @@ struct POp {
   int n_fused = 0;                        // tree steps folded into this launch besides its own
   BitsNDesc nd{};                         // descriptor of a fused step (k_merge_bits_n)
   BitsFDesc fd{};                         // ... or of its factored form (k_merge_bits_f), when use_f
+  long wf_chosen = 0, wf_default = 0;     // modelled L1 wavefronts per work item (make_bits_f_desc)
   double launch_entries = 0;              // fused step: entries the launch must read and write (operands + result)
   bool use_f = false;
   int n_operands() const { return kind == OP_STEP ? 2 + (int)xn.size() : 1; }
@@ -740,8 +741,8 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
             int n_slab_bits = 0;
             if (P.nodes[y].shared)
               for (auto w : P.nodes[y].slab) n_slab_bits += ilog2(P.wext[w]);
-            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits);
-            if (f.ok) { op.fd = f.d; op.use_f = true; }
+            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 1.0) != 0.0);
+            if (f.ok) { op.fd = f.d; op.use_f = true; op.wf_chosen = f.wf_chosen; op.wf_default = f.wf_default; }
           }
           P.info.n_fused_steps += op.n_fused;
         }
@@ -1202,7 +1203,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"wf\":" << op.wf_chosen << ",\"wf_default\":" << op.wf_default << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {
