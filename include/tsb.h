@@ -185,6 +185,8 @@ typedef struct {
  *   TSB_FUSE_MIN_LOG2 (22)   consecutive packed steps are fused across intermediates of at least 2^x entries
  *   TSB_FUSE_MAX_K (2)       summed wires per fused launch (-1: never fuse)
  *   TSB_FUSE_PAIR (1)        pair wires of k_merge_bits_f (0: none, -1: k_merge_bits_n only)
+ *   TSB_FUSE_LANES (0)       1: k_merge_bits_f picks the wires that index a warp's lanes by a wavefront model
+ *                            (measured 2 % slower on the n=50 bench: off)
  *   TSB_CHAIN_MAX_OPS (2)    waves of at most this many small ops join a single-CTA chain launch (0: off)
  *   TSB_PRE_RESTRICT (1)     0: a rank computes the once-only tensors in full whatever its slice block
  *   TSB_PERMUTE_T4 (1)       0: never use the 4x4 register-transpose permute kernel */

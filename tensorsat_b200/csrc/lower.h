@@ -542,7 +542,7 @@ struct BitsFArgs {
 };
 
 inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
-                                  int n_top_excluded = 0, bool choose_lanes = true) {
+                                  int n_top_excluded = 0, bool choose_lanes = false) {
   BitsFArgs m;
   const int R = (int)out_bits.size(), n = (int)operands.size();
   if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;

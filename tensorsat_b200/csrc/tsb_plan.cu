@@ -741,7 +741,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
             int n_slab_bits = 0;
             if (P.nodes[y].shared)
               for (auto w : P.nodes[y].slab) n_slab_bits += ilog2(P.wext[w]);
-            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 1.0) != 0.0);
+            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 0.0) != 0.0);
             if (f.ok) { op.fd = f.d; op.use_f = true; op.wf_chosen = f.wf_chosen; op.wf_default = f.wf_default; }
           }
           P.info.n_fused_steps += op.n_fused;
