@@ -833,3 +833,36 @@ def test_slice_blocks_restrict_the_once_only_tensors():
         r = torch.zeros_like(full)
         plan.execute(leaves, r, 1, 3)
         assert plan.describe()["restricted_launches"] == 0
+
+
+def test_first_model_reproduces_the_reference_traces():
+    """``AssignmentSearch`` (one plan, leaves swapped per decision) against the reference notebooks: the sat / unsat
+    trace of 01-introduction.ipynb:1848-1849 (G5), the lexicographically first model of 02-random-ksat.ipynb:707 (G4,
+    on the GPU only: 30 executions of a width-18 plan are slow on the emulation), brute force otherwise."""
+    from tensorsat_b200 import _native
+    from tensorsat_b200.lib.search import AssignmentSearch
+
+    cnf = CNFInstance.random(3, 3, 6, rng=3)
+    search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring()))
+    trace = []
+    assert search.first_model(lambda spec, ok: trace.append((spec, ok))) == "011"
+    assert trace == [("???", True), ("0??", True), ("00?", False), ("01?", True), ("010", False), ("011", True)]
+    if _native._device == "cuda":
+        cnf = CNFInstance.random(4, 20, 195, rng=1)
+        search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2))
+        assert search.first_model() == "10011001000011100101" and search.decisions == 30
+    n = 11
+    cnf = CNFInstance.random(3, n, 44, rng=2)
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape(-1)
+    search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2))
+    want = format(int(np.flatnonzero(brute)[0]), "b").rjust(n, "0") if brute.any() else None
+    assert search.first_model() == want
+    import os
+
+    from tests.conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "kissat", "full2.cnf")) as f:
+        unsat = CNFInstance.from_dimacs(f.read())
+    assert AssignmentSearch(unsat, TreeContraction(CudaFinRel, unsat.contraction_wiring())).first_model() is None
+    with pytest.raises(ValueError):
+        search.satisfiable("0" * (n - 1))
