@@ -122,6 +122,9 @@ struct tsb_plan {
   int rr_nfixed = 0;
   std::vector<int64_t> rr_digits;
   int rr_launches = 0;  // sub-block launches of the last execution (reported by tsb_plan_describe)
+  // side streams for the mutually independent launches of one wave of the once-only schedule (fork / join)
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> side_ev;   // [0] fork, [1 + i] join of side stream i
   int mode = TSB_SAT;
   uint32_t flags = 0;
   int n_leaves = 0, n_wires = 0;
@@ -1292,44 +1295,98 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
     }
     for (int g : P.gathered_nodes) TSB_CUDA(cudaMemsetAsync(base + P.nodes[g].offset, 0, P.nodes[g].bytes, stream));
     // once-only parts: waves of independent ops (small ops of a wave = one launch)
-    auto run_schedule = [&](std::vector<Launch>& sched) {
-      for (size_t li = 0; li < sched.size(); li++) {
-        Launch& l = sched[li];
-        l.last_ms = 0;
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (timing) {
-          TSB_CUDA(cudaEventCreate(&t0));
-          TSB_CUDA(cudaEventCreate(&t1));
-          TSB_CUDA(cudaEventRecord(t0, stream));
-        }
-        if (l.op < 0) {
-          const int n = l.batch_end - l.batch_begin;
-          if (l.chain)
-            TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, stream,
-                       (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
-          else
-            TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, stream,
-                       (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
-          ctx->launches++;
-          TSB_CUDA(cudaGetLastError());
+    // An op may run on a side stream when its launch needs nothing but its descriptor and the arena block: packed
+    // steps, conversions and aligned byte merges (the other paths take temporaries from the stream-ordered arena).
+    auto forkable = [&](const Launch& l) {
+      if (l.op < 0) return false;
+      const POp& op = P.ops[l.op];
+      if (op.kind == OP_LEAF || P.nodes[op.out].is_out) return false;
+      if (op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND) return true;
+      if (op.kind != OP_STEP) return false;
+      if (op.use_bits) return true;
+      if (!op.use_merge || op.use_gemm) return false;
+      const PNode& a = P.nodes[op.lhs];
+      const PNode& b = P.nodes[op.rhs];
+      const PNode& o = P.nodes[op.out];
+      const uintptr_t al = ((uintptr_t)dtype_size(a.dtype) << __builtin_popcount((unsigned)op.md.nibL)) - 1;
+      const uintptr_t ar = ((uintptr_t)dtype_size(b.dtype) << __builtin_popcount((unsigned)op.md.nibR)) - 1;
+      return !a.is_out && !b.is_out && ((uintptr_t)a.offset & al) == 0 && ((uintptr_t)b.offset & ar) == 0 &&
+             ((uintptr_t)o.offset & 15) == 0 && P.rr_nfixed == 0;
+    };
+    static const int n_side_max = [] { const char* e = getenv("TSB_WAVE_STREAMS"); return e ? atoi(e) : 4; }();
+    auto run_one = [&](Launch& l, cudaStream_t st) {
+      l.last_ms = 0;
+      cudaEvent_t t0 = nullptr, t1 = nullptr;
+      if (timing) {
+        TSB_CUDA(cudaEventCreate(&t0));
+        TSB_CUDA(cudaEventCreate(&t1));
+        TSB_CUDA(cudaEventRecord(t0, st));
+      }
+      if (l.op < 0) {
+        const int n = l.batch_end - l.batch_begin;
+        if (l.chain)
+          TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, st,
+                         (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
+        else
+          TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, st,
+                         (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
+        ctx->launches++;
+        TSB_CUDA(cudaGetLastError());
+      } else {
+        POp& op = P.ops[l.op];
+        if (op.kind == OP_LEAF) {
+          if (!(P.n_leaves == 1 && !P.sliced.empty())) run_leaf(P, op, base, leaf_ptrs[op.leaf], out, st);
         } else {
-          POp& op = P.ops[l.op];
-          if (op.kind == OP_LEAF) {
-            if (!(P.n_leaves == 1 && !P.sliced.empty())) run_leaf(P, op, base, leaf_ptrs[op.leaf], out, stream);
-          } else {
-            run_step(P, op, base, out, nullptr, false, stream);
-          }
+          run_step(P, op, base, out, nullptr, false, st);
         }
-        if (timing) {
-          TSB_CUDA(cudaEventRecord(t1, stream));
-          TSB_CUDA(cudaEventSynchronize(t1));
-          float ms = 0;
-          TSB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-          l.last_ms = ms;
-          if (l.op >= 0) P.ops[l.op].last_ms = ms;
-          cudaEventDestroy(t0);
-          cudaEventDestroy(t1);
+      }
+      if (timing) {
+        TSB_CUDA(cudaEventRecord(t1, st));
+        TSB_CUDA(cudaEventSynchronize(t1));
+        float ms = 0;
+        TSB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+        l.last_ms = ms;
+        if (l.op >= 0) P.ops[l.op].last_ms = ms;
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+      }
+    };
+    // once-only parts: waves of independent ops (small ops of a wave = one launch; the other launches of a wave are
+    // spread over the caller's stream and a few side streams, joined before the next wave)
+    auto run_schedule = [&](std::vector<Launch>& sched) {
+      size_t li = 0;
+      while (li < sched.size()) {
+        size_t lj = li;
+        if (!timing && n_side_max > 0 && forkable(sched[li]))
+          while (lj < sched.size() && sched[lj].wave == sched[li].wave && forkable(sched[lj])) lj++;
+        const int group = (int)(lj - li);
+        if (group < 3) {
+          run_one(sched[li], stream);
+          li++;
+          continue;
         }
+        const int n_side = std::min(n_side_max, group - 1);
+        while ((int)P.side.size() < n_side) {
+          cudaStream_t st;
+          TSB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+          P.side.push_back(st);
+        }
+        while ((int)P.side_ev.size() < 1 + n_side) {
+          cudaEvent_t e;
+          TSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          P.side_ev.push_back(e);
+        }
+        TSB_CUDA(cudaEventRecord(P.side_ev[0], stream));
+        for (int q = 0; q < n_side; q++) TSB_CUDA(cudaStreamWaitEvent(P.side[q], P.side_ev[0], 0));
+        for (int g = 0; g < group; g++) {
+          const int lane = g % (n_side + 1);
+          run_one(sched[li + g], lane == 0 ? stream : P.side[lane - 1]);
+        }
+        for (int q = 0; q < n_side; q++) {
+          TSB_CUDA(cudaEventRecord(P.side_ev[1 + q], P.side[q]));
+          TSB_CUDA(cudaStreamWaitEvent(stream, P.side_ev[1 + q], 0));
+        }
+        li = lj;
       }
     };
     // A rank that executes an aligned power-of-two block of slice ids computes only its own sub-blocks of the
@@ -1413,6 +1470,8 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
 int tsb_plan_destroy(tsb_plan* plan) {
   if (plan) {
     for (auto e : plan->ev) cudaEventDestroy(e);
+    for (auto e : plan->side_ev) cudaEventDestroy(e);
+    for (auto st : plan->side) cudaStreamDestroy(st);
     if (plan->d_small_ops) cudaFree(plan->d_small_ops);
     if (plan->d_ptrs) cudaFree(plan->d_ptrs);
     delete plan;
