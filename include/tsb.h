@@ -188,6 +188,10 @@ typedef struct {
  *   TSB_FUSE_LANES (0)       1: k_merge_bits_f picks the wires that index a warp's lanes by a wavefront model
  *                            (measured 2 % slower on the n=50 bench: off)
  *   TSB_CHAIN_MAX_OPS (2)    waves of at most this many small ops join a single-CTA chain launch (0: off)
+ *   TSB_WAVE_STREAMS (0)     n > 0: the independent launches of one wave of the once-only schedule are spread over
+ *                            the caller's stream and n side streams (fork / join); measured with 4 on the n=50
+ *                            bench: device time -1.5 %, end-to-end time +1.6 % (more host work before the first
+ *                            kernel of a step): off
  *   TSB_PRE_RESTRICT (1)     0: a rank computes the once-only tensors in full whatever its slice block
  *   TSB_PERMUTE_T4 (1)       0: never use the 4x4 register-transpose permute kernel */
 

@@ -1313,7 +1313,7 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       return !a.is_out && !b.is_out && ((uintptr_t)a.offset & al) == 0 && ((uintptr_t)b.offset & ar) == 0 &&
              ((uintptr_t)o.offset & 15) == 0 && P.rr_nfixed == 0;
     };
-    static const int n_side_max = [] { const char* e = getenv("TSB_WAVE_STREAMS"); return e ? atoi(e) : 4; }();
+    static const int n_side_max = [] { const char* e = getenv("TSB_WAVE_STREAMS"); return e ? atoi(e) : 0; }();
     auto run_one = [&](Launch& l, cudaStream_t st) {
       l.last_ms = 0;
       cudaEvent_t t0 = nullptr, t1 = nullptr;
