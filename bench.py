@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 N_VARS, N_CLAUSES, SEED, K_SAT = 50, 213, 0, 3
 TARGET_LOG2 = 30
-PLAN_FILE = os.path.join(ROOT, "bench_plans", f"c1_n50_m213_seed0_w{TARGET_LOG2}.json")
+PLAN_FILE = os.environ.get("TSB_BENCH_PLAN") or os.path.join(ROOT, "bench_plans", f"c1_n50_m213_seed0_w{TARGET_LOG2}.json")
 WORKLOAD = (f"random {K_SAT}-SAT n={N_VARS} m={N_CLAUSES} seed={SEED}, SAT decision (all inputs unknown), "
             f"bintree network, elimination-order tree sliced to 2^{TARGET_LOG2}-entry intermediates")
 
