@@ -140,13 +140,19 @@ def hbm_peak() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
+_FINE: dict = {}
+
+
 def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22) -> dict:
     """The reference arithmetic (numpy oracle) on a bounded sample of the same plan: the tree is sliced
     further so that one slice fits the host comfortably, `n_sample` slices are timed and the whole-job
     time is extrapolated (slices have identical shapes and cost)."""
     from oracle import fin_rel_oracle as O
 
-    fine = tree.with_sliced(()).slice_to(target_log2)
+    key = (id(tree), target_log2)
+    if key not in _FINE:   # slicing the tree to host size takes seconds: once per run, not once per step
+        _FINE[key] = tree.with_sliced(()).slice_to(target_log2)
+    fine = _FINE[key]
     leaves = [b.tensor for b in diagram.boxes]
     n = fine.num_slices
     ids = [int(i * n / n_sample) for i in range(n_sample)]

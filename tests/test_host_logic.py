@@ -137,6 +137,21 @@ def test_tree_search_and_slicing():
         ContractionTree(net, ((0, 0),) + e.ssa_path[1:])
 
 
+def test_annealed_elimination_order_is_valid_and_never_worse():
+    """The opt-in annealing of the order's tail (planner/search.py) is deterministic for a seed, returns a valid
+    tree over the same network, and is kept only when the real objective improves."""
+    from tensorsat_b200.planner.search import _objective
+
+    c = CNFInstance.random(3, 30, 128, rng=1)
+    net = Network.from_diagram((c.inputs(None) >> c.diagram()).flatten())
+    base = find_tree_elimination(net, trials=2, seed=0)
+    a = find_tree_elimination(net, trials=2, seed=0, anneal_iters=3000, anneal_tail=30, anneal_restarts=2)
+    b = find_tree_elimination(net, trials=2, seed=0, anneal_iters=3000, anneal_tail=30, anneal_restarts=2)
+    assert a.ssa_path == b.ssa_path
+    assert a.network == net and a.stats().num_contractions == net.num_leaves - 1
+    assert _objective(a, "combo", None) <= _objective(base, "combo", None)
+
+
 def test_slice_blocks_partition_all_slices():
     from tensorsat_b200.distributed import slice_block
 
