@@ -825,8 +825,7 @@ def test_slice_blocks_restrict_the_once_only_tensors():
                 r = torch.zeros_like(full)
                 plan.execute(leaves, r, lo, lo + size)
                 parts.append(r.cpu().numpy().reshape(want.shape).copy())
-            if mode == _native.MODE_SAT:
-                assert plan.describe()["restricted_launches"] > 0
+            assert plan.describe()["restricted_launches"] > 0   # packed steps / conversions (SAT), typed merges (counting)
             comb = np.bitwise_or.reduce(parts) if mode == _native.MODE_SAT else np.sum(parts, axis=0)
             assert np.array_equal(comb, want), (mode, size)
         # an unaligned range is executed without the restriction
