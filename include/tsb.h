@@ -70,6 +70,11 @@ int tsb_ctx_create(int device, tsb_ctx** ctx);
 int tsb_ctx_destroy(tsb_ctx* ctx);
 /* Number of kernels launched through this context since creation (bench "gpu_launches"). */
 int tsb_ctx_launch_count(tsb_ctx* ctx, int64_t* count);
+/* Per-kernel launch counts: tsb_ctx_trace(ctx, 1) clears the counters and starts counting, tsb_ctx_trace_json
+ * returns {"kernel name": launches, ...} (names as in DESIGN.md 3.2, e.g. "k_permute<4>", "k_merge_bits_f",
+ * "k_gemm_i8").  Tests and smoke() use it to prove which kernels served a call. */
+int tsb_ctx_trace(tsb_ctx* ctx, int enabled);
+int tsb_ctx_trace_json(tsb_ctx* ctx, char* buf, size_t cap, size_t* needed);
 
 /* ---- caching device allocator for intermediates (north-star item (d)) ------------------- */
 typedef struct {
@@ -148,6 +153,9 @@ int tsb_contract2_bits(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_
 /* result = 1 iff every one of the n elements equals 1.  Synchronises the stream. */
 int tsb_all_ones(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result,
                  tsb_stream stream);
+/* result = 1 iff every one of the n elements is 0 or 1 (the value check of FinRel.__new__,
+ * tensorsat/lang/fin_rel.py:119-121, for device-resident tensors).  Synchronises the stream. */
+int tsb_all_binary(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result, tsb_stream stream);
 /* Reads one element back as int64.  Synchronises the stream. */
 int tsb_scalar_to_host(tsb_ctx* ctx, const void* ptr, int dtype, int64_t* out, tsb_stream stream);
 

@@ -83,10 +83,10 @@ class PlanInfo(C.Structure):
 
 
 EXPORTS = [
-    "tsb_version", "tsb_last_error", "tsb_ctx_create", "tsb_ctx_destroy", "tsb_ctx_launch_count",
+    "tsb_version", "tsb_last_error", "tsb_ctx_create", "tsb_ctx_destroy", "tsb_ctx_launch_count", "tsb_ctx_trace", "tsb_ctx_trace_json",
     "tsb_arena_reserve", "tsb_arena_alloc", "tsb_arena_release", "tsb_arena_trim", "tsb_arena_stats",
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
-    "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
+    "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_all_binary", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
     "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",
     "tsb_plan_destroy", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
 ]
@@ -286,10 +286,33 @@ def all_ones(t: Any, mode: int) -> bool:
     return bool(res.value)
 
 
+def all_binary(t: Any) -> bool:
+    """True iff every element of the device tensor is 0 or 1 (one kernel, one synchronising read-back)."""
+    res = C.c_int(0)
+    _check(lib().tsb_all_binary(ctx(), _ptr(t), C.c_int64(t.numel()), dtype_code(t), C.byref(res), stream()))
+    return bool(res.value)
+
+
 def launch_count() -> int:
     n = C.c_int64(0)
     _check(lib().tsb_ctx_launch_count(ctx(), C.byref(n)))
     return int(n.value)
+
+
+def trace(enabled: bool = True) -> None:
+    """Clears and (re)starts the per-kernel launch counters of the current context."""
+    _check(lib().tsb_ctx_trace(ctx(), int(bool(enabled))))
+
+
+def kernel_counts() -> dict[str, int]:
+    """``{kernel name: launches}`` since the last ``trace()``."""
+    import json
+
+    need = C.c_size_t(0)
+    _check(lib().tsb_ctx_trace_json(ctx(), None, C.c_size_t(0), C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(lib().tsb_ctx_trace_json(ctx(), buf, need, C.byref(need)))
+    return json.loads(buf.value.decode())
 
 
 def arena_stats() -> dict[str, int]:

@@ -129,6 +129,10 @@ class TreeContraction(Contraction):
         if isinstance(box, CudaFinRel):
             return box.device_tensor
         if isinstance(box, CudaCountRel):
+            if not box.is_binary():
+                # a plan stages its leaves as 0/1 bytes and sizes every intermediate from that bound
+                raise ValueError("TreeContraction counts over 0/1 relation tensors: a leaf box has entries other "
+                                 "than 0 and 1 (contract weighted tensors step by step with SimpleContraction).")
             t = box.device_tensor
             u8 = _native.empty(t.numel(), 0)
             _native.widen(t.reshape(-1), u8)
@@ -158,7 +162,10 @@ class TreeContraction(Contraction):
         plan = self.plan()
         if len(leaves) != plan.n_leaves:
             raise ValueError(f"Expected {plan.n_leaves} leaf arrays, got {len(leaves)}.")
-        st = getattr(self, "_staging", None)
+        # staging buffers live on one device: keyed by the device that is current for this call
+        stagings = self.__dict__.setdefault("_stagings", {})
+        dev_key = str(_native.device())
+        st = stagings.get(dev_key)
         if st is None:
             sizes = [int(np.asarray(a).size) for a in leaves]
             total = int(sum(sizes))
@@ -173,7 +180,7 @@ class TreeContraction(Contraction):
             import ctypes
 
             ptrs = (ctypes.c_void_p * len(leaves))(*[dev.data_ptr() + int(o) for o in offs])
-            st = self._staging = (pin, dev, res, sizes, ptrs)
+            st = stagings[dev_key] = (pin, dev, res, sizes, ptrs)
         pin, dev, res, sizes, ptrs = st
         # one pass over the leaves: C-order bytes of every array, joined (uint8 / bool arrays are taken as they
         # are; anything else, or a leaf of another size, shows as a length mismatch and takes the checked path)
@@ -191,9 +198,18 @@ class TreeContraction(Contraction):
         lo, hi = (0, plan.info["n_slices"]) if slice_range is None else slice_range
         plan.execute_ptrs(ptrs, out.data_ptr(), lo, hi)
         res.copy_(out, non_blocking=False)
-        dims = tuple(self.wiring.wire_dims[w] for w in self.wiring.out_wires)
+        # the plan contracts onto the DISTINCT output wires; repeated output wires tie axes to a diagonal
+        # (what contract() does with _rewire; simple.py:287-289)
+        dims = tuple(self.wiring.wire_dims[w] for w in self._distinct_out)
         self.h2d_bytes, self.d2h_bytes = int(pin.numel()), int(res.numel() * res.element_size())
-        return res.numpy().reshape(dims).copy()
+        arr = res.numpy().reshape(dims).copy()
+        if self._distinct_out != tuple(self.wiring.out_wires):
+            ports = [self._distinct_out.index(w) for w in self.wiring.out_wires]
+            full = np.zeros(tuple(dims[p] for p in ports), dtype=arr.dtype)
+            for idx in np.ndindex(*dims):
+                full[tuple(idx[p] for p in ports)] = arr[idx]
+            arr = full
+        return arr
 
     def contract(self, diagram: Diagram, *, slice_range: tuple[int, int] | None = None, **_ignored: Any) -> Box:
         """Validates and contracts the given diagram (cotengra.py:100-128).

@@ -233,4 +233,15 @@ k_all_ones(const void* __restrict__ p, int dt, int64_t n, int* __restrict__ flag
   if (!ok) *flag = 0;
 }
 
+// flag (pre-set to 1) is cleared if any element is neither 0 nor 1: the validation of FinRel.__new__
+// (tensorsat/lang/fin_rel.py:119-121, "Values in a Boolean tensor must be 0 or 1.") for device-resident leaves
+static __global__ void __launch_bounds__(256)
+k_all_binary(const void* __restrict__ p, int dt, int64_t n, int* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool ok = true;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    ok = ok && ((uint64_t)load_as_i64(p, dt, i) <= 1);
+  if (!ok) *flag = 0;
+}
+
 }  // namespace tsb

@@ -86,6 +86,13 @@ struct tsb_ctx {
   int device = 0;
   int sm_count = 148;
   int64_t launches = 0;
+  // per-kernel launch counts since tsb_ctx_trace(ctx, 1) (tests and smoke() prove which kernels ran)
+  bool trace = false;
+  std::map<std::string, int64_t> kcount;
+  void note(const char* kernel) {
+    launches++;
+    if (trace) kcount[kernel]++;
+  }
   tsb::Arena arena;
   int* d_flag = nullptr;  // scratch for all_ones
   uint8_t* d_one = nullptr;  // the u8 scalar 1
@@ -182,7 +189,7 @@ inline void launch_generic(tsb_ctx* ctx, const GenDesc& g, const void* lhs, cons
             (long long)g.n_out_iter, (long long)g.n_red_iter);
   const int grid = grid_for(ctx, g.n_out_iter, 256);
   TSB_LAUNCH_PDL(k_generic, dim3(grid), dim3(256), 0, stream, g, lhs, rhs, out);
-  ctx->launches++;
+  ctx->note("k_generic");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -318,7 +325,7 @@ inline void launch_permute_t4(tsb_ctx* ctx, const PermT4Desc& d, const void* src
   const size_t smem = perm_t4_smem_bytes(d.p);
   const int grid = (int)std::min<int64_t>(d.p.n_tiles, (int64_t)ctx->sm_count * 8);
   TSB_LAUNCH(k_permute_t4, dim3(grid), dim3(kPermThreads), smem, stream, d, (const uint8_t*)src, (uint8_t*)dst);
-  ctx->launches++;
+  ctx->note("k_permute_t4");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -339,7 +346,7 @@ inline void launch_permute_fast(tsb_ctx* ctx, const PermDesc& d, int G, const vo
     case 8: TSB_LAUNCH(k_permute<8>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
     default: TSB_LAUNCH(k_permute<16>, dim3(grid), dim3(kPermThreads), smem, stream, d, s, t); break;
   }
-  ctx->launches++;
+  ctx->note(G == 1 ? "k_permute<1>" : G == 2 ? "k_permute<2>" : G == 4 ? "k_permute<4>" : G == 8 ? "k_permute<8>" : "k_permute<16>");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -724,7 +731,7 @@ inline void launch_merge_t(tsb_ctx* ctx, const MergeDesc& d, const void* l, cons
     TSB_LAUNCH(kc, dim3(grid), dim3(kMergeThreads), 0, stream, d, (const TL*)l, (const TR*)r, (TO*)o);
   else
     TSB_LAUNCH(kn, dim3(grid), dim3(kMergeThreads), 0, stream, d, (const TL*)l, (const TR*)r, (TO*)o);
-  ctx->launches++;
+  ctx->note("k_merge");
   TSB_CUDA(cudaGetLastError());
 }
 

@@ -322,7 +322,7 @@ void gemm_u8_impl(tsb_ctx* ctx, const void* A, const void* B, void* C, int b_bit
   }
   const int grid = (int)std::min<int64_t>(p.num_tiles, ctx->sm_count);
   k_gemm_i8<<<grid, kGemmThreads, smem, stream>>>(ma, mb, p, C);
-  ctx->launches++;
+  ctx->note("k_gemm_i8");
   TSB_CUDA(cudaGetLastError());
 }
 

@@ -46,7 +46,7 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
     const int gw = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
     if (d.kbits == 0) bits_w_l<0>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream);
     else bits_w_l<1>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream);
-    ctx->launches++;
+    ctx->note("k_merge_bits_w");
     TSB_CUDA(cudaGetLastError());
     return;
   }
@@ -59,7 +59,7 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
   else
     TSB_LAUNCH_PDL(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
                (const uint32_t*)r, bitoff_r, (uint4*)o);
-  ctx->launches++;
+  ctx->note("k_merge_bits");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -96,7 +96,7 @@ void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* pt
   if (d.n_ops == 2) bits_n_k<2>(ctx, d, pp, o, grid, stream);
   else if (d.n_ops == 3) bits_n_k<3>(ctx, d, pp, o, grid, stream);
   else bits_n_k<4>(ctx, d, pp, o, grid, stream);
-  ctx->launches++;
+  ctx->note("k_merge_bits_n");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -104,7 +104,7 @@ void launch_pack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entrie
   const int64_t n_words = (n_entries + 31) >> 5;
   const int grid = (int)std::min<int64_t>((n_words + 255) / 256, (int64_t)ctx->sm_count * 16);
   TSB_LAUNCH_PDL(k_pack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint8_t*)src, (uint32_t*)dst, n_entries);
-  ctx->launches++;
+  ctx->note("k_pack_bits");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -116,7 +116,7 @@ void launch_pack_map(tsb_ctx* ctx, const void* src, bool src_packed, void* dst, 
     TSB_LAUNCH_PDL(k_pack_map<true>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
   else
     TSB_LAUNCH_PDL(k_pack_map<false>, dim3(grid), dim3(256), 0, stream, src, (uint32_t*)dst, n_entries, lo, hi);
-  ctx->launches++;
+  ctx->note("k_pack_map");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -126,7 +126,7 @@ void launch_unpack_bits(tsb_ctx* ctx, const void* src, void* dst, int64_t n_entr
   const int grid = (int)std::min<int64_t>((n_vec + 255) / 256, (int64_t)ctx->sm_count * 16);
   TSB_LAUNCH_PDL(k_unpack_bits, dim3(std::max(grid, 1)), dim3(256), 0, stream, (const uint32_t*)src, (uint8_t*)dst,
              n_entries, accumulate ? 1 : 0);
-  ctx->launches++;
+  ctx->note("k_unpack_bits");
   TSB_CUDA(cudaGetLastError());
 }
 

@@ -35,7 +35,7 @@ void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* pt
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (d.n_pair ? 2 : 3)));
   TSB_LAUNCH_PDL(k, dim3(grid), dim3(kBitsFThreads), 0, stream, d, pp, (uint4*)o);
-  ctx->launches++;
+  ctx->note("k_merge_bits_f");
   TSB_CUDA(cudaGetLastError());
 }
 

@@ -11,7 +11,7 @@ static void cnt_one(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void*
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 6);
     auto k = k_merge_cnt<NL, NR, int32_t, uint8_t>;
     TSB_LAUNCH(k, dim3(grid), dim3(kCntThreads), 0, stream, d, (const int32_t*)l, (const uint8_t*)r, (int32_t*)o);
-    ctx->launches++;
+    ctx->note("k_merge_cnt");
     TSB_CUDA(cudaGetLastError());
   } else {
     TSB_CHECK(false, TSB_ERR_INVALID, "internal: output lane covered by neither operand");

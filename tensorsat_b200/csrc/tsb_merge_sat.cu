@@ -25,7 +25,7 @@ static void launch_one(tsb_ctx* ctx, const MergeSatDesc& dd, const void* l, cons
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
     auto k = k_merge_sat<NL, NR>;
     TSB_LAUNCH_PDL(k, dim3(grid), dim3(kSatThreads), 0, stream, dd, (const uint8_t*)l, (const uint8_t*)r, (uint8_t*)o);
-    ctx->launches++;
+    ctx->note("k_merge_sat");
     TSB_CUDA(cudaGetLastError());
   } else {
     TSB_CHECK(false, TSB_ERR_INVALID, "internal: output lane covered by neither operand");

@@ -10,7 +10,7 @@ static void wide_one(tsb_ctx* ctx, const MergeDesc& d, const void* l, const void
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
   auto k = k_merge_wide<TL, TR>;
   TSB_LAUNCH(k, dim3(grid), dim3(kWideThreads), 0, stream, d, (const TL*)l, (const TR*)r, (int64_t*)o);
-  ctx->launches++;
+  ctx->note("k_merge_wide");
   TSB_CUDA(cudaGetLastError());
 }
 

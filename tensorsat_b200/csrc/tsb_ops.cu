@@ -202,13 +202,13 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
             if (c_can == ob) {
               TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n_out, 256)), dim3(256), 0, stream, (const void*)src, gemm_dt, out,
                          dout, n_out, 0);
-              ctx->launches++;
+              ctx->note("k_convert");
               return;
             }
             tc2.reset(new Temp(ctx, (size_t)dtype_size(dout) << ob.size()));
             TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n_out, 256)), dim3(256), 0, stream, (const void*)src, gemm_dt,
                        tc2->p, dout, n_out, 0);
-            ctx->launches++;
+            ctx->note("k_convert");
             src = tc2->p;
           }
           permute_bits(ctx, src, c_can, out, ob, dtype_size(dout), stream);
@@ -388,6 +388,29 @@ int tsb_ctx_launch_count(tsb_ctx* ctx, int64_t* count) {
   TSB_API_END
 }
 
+int tsb_ctx_trace(tsb_ctx* ctx, int enabled) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  ctx->trace = enabled != 0;
+  ctx->kcount.clear();
+  TSB_API_END
+}
+
+int tsb_ctx_trace_json(tsb_ctx* ctx, char* buf, size_t cap, size_t* needed) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  TSB_CHECK(needed != nullptr, TSB_ERR_INVALID, "null argument");
+  std::string s = "{";
+  for (auto& kv : ctx->kcount) {
+    if (s.size() > 1) s += ",";
+    s += "\"" + kv.first + "\":" + std::to_string(kv.second);
+  }
+  s += "}";
+  *needed = s.size() + 1;
+  if (buf && cap >= s.size() + 1) memcpy(buf, s.c_str(), s.size() + 1);
+  TSB_API_END
+}
+
 int tsb_arena_reserve(tsb_ctx* ctx, size_t bytes) {
   TSB_API_BEGIN
   check_ctx(ctx);
@@ -524,7 +547,7 @@ int tsb_union(tsb_ctx* ctx, const void* a, const void* b, void* out, int64_t n, 
                  (uint8_t*)out, n);
       TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (const void*)out, (int)TSB_U8, out,
                  (int)TSB_U8, n, 1);
-      ctx->launches++;
+      ctx->note("k_convert");
     }
   } else if (dtype == TSB_U8) {
     TSB_LAUNCH(k_add<uint8_t>, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (const uint8_t*)a, (const uint8_t*)b,
@@ -536,7 +559,7 @@ int tsb_union(tsb_ctx* ctx, const void* a, const void* b, void* out, int64_t n, 
     TSB_LAUNCH(k_add<int64_t>, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (const int64_t*)a, (const int64_t*)b,
                (int64_t*)out, n);
   }
-  ctx->launches++;
+  ctx->note("k_union");
   TSB_CUDA(cudaGetLastError());
   TSB_API_END
 }
@@ -546,7 +569,7 @@ static void fill_impl(tsb_ctx* ctx, void* dst, int64_t n, int64_t value, int dty
   if (dtype == TSB_U8) TSB_LAUNCH(k_fill<uint8_t>, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (uint8_t*)dst, n, (uint8_t)value);
   else if (dtype == TSB_I32) TSB_LAUNCH(k_fill<int32_t>, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (int32_t*)dst, n, (int32_t)value);
   else TSB_LAUNCH(k_fill<int64_t>, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, (int64_t*)dst, n, (int64_t)value);
-  ctx->launches++;
+  ctx->note("k_fill");
   TSB_CUDA(cudaGetLastError());
 }
 
@@ -580,7 +603,7 @@ int tsb_spider(tsb_ctx* ctx, void* dst, int dim, int num_ports, int dtype, tsb_s
   if (dtype == TSB_U8) TSB_LAUNCH(k_diag_ones<uint8_t>, dim3(grid), dim3(128), 0, s, (uint8_t*)dst, dim, diag);
   else if (dtype == TSB_I32) TSB_LAUNCH(k_diag_ones<int32_t>, dim3(grid), dim3(128), 0, s, (int32_t*)dst, dim, diag);
   else TSB_LAUNCH(k_diag_ones<int64_t>, dim3(grid), dim3(128), 0, s, (int64_t*)dst, dim, diag);
-  ctx->launches++;
+  ctx->note("k_diag_ones");
   TSB_CUDA(cudaGetLastError());
   TSB_API_END
 }
@@ -593,7 +616,7 @@ int tsb_convert(tsb_ctx* ctx, const void* src, int src_dtype, void* dst, int dst
   if (n <= 0) return TSB_OK;
   TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n, 256)), dim3(256), 0, (cudaStream_t)stream, src, src_dtype, dst,
              dst_dtype, n, clamp);
-  ctx->launches++;
+  ctx->note("k_convert");
   TSB_CUDA(cudaGetLastError());
   TSB_API_END
 }
@@ -651,7 +674,23 @@ int tsb_all_ones(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* resul
   TSB_CUDA(cudaMemcpyAsync(ctx->d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, s));
   if (n > 0) {
     TSB_LAUNCH(k_all_ones, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, ptr, dtype, n, ctx->d_flag);
-    ctx->launches++;
+    ctx->note("k_all_ones");
+  }
+  TSB_CUDA(cudaMemcpyAsync(result, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  TSB_CUDA(cudaStreamSynchronize(s));
+  TSB_API_END
+}
+
+int tsb_all_binary(tsb_ctx* ctx, const void* ptr, int64_t n, int dtype, int* result, tsb_stream stream) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  check_dtype(dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  int one = 1;
+  TSB_CUDA(cudaMemcpyAsync(ctx->d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+  if (n > 0) {
+    TSB_LAUNCH(k_all_binary, dim3(grid_for(ctx, n, 256)), dim3(256), 0, s, ptr, dtype, n, ctx->d_flag);
+    ctx->note("k_all_binary");
   }
   TSB_CUDA(cudaMemcpyAsync(result, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   TSB_CUDA(cudaStreamSynchronize(s));

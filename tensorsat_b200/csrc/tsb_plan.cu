@@ -1330,7 +1330,7 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
         else
           TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, st,
                          (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
-        ctx->launches++;
+        ctx->note(l.chain ? "k_small_chain" : "k_small_batch");
         TSB_CUDA(cudaGetLastError());
       } else {
         POp& op = P.ops[l.op];

@@ -81,6 +81,7 @@ class _CudaTensorBox(TensorLikeBox):
         dev: Any = None,
         axes: Sequence[int] | None = None,
         name: str | None = None,
+        binary: bool | None = None,
     ) -> Self:
         if cls in (_CudaTensorBox,):
             raise TypeError("Only final subclasses of Box can be instantiated.")
@@ -91,6 +92,9 @@ class _CudaTensorBox(TensorLikeBox):
         self._dev = dev
         self._axes = None if axes is None else tuple(int(a) for a in axes)
         self._hash_cache = None
+        # every entry is 0 or 1: always for the boolean semiring; for counting boxes known for host-built ones,
+        # checked on the device on demand otherwise (is_binary)
+        self._binary = True if cls._MODE == MODE_SAT else binary
         return self
 
     def __new__(cls, tensor: Any) -> Self:
@@ -115,7 +119,7 @@ class _CudaTensorBox(TensorLikeBox):
             raise ValueError("Zero dimension in shape.")
         arr = arr.astype(cls._NP_DTYPE, copy=True)
         arr.setflags(write=False)
-        return cls._new(arr.shape, host=arr)
+        return cls._new(arr.shape, host=arr, binary=bool(arr.size == 0 or (arr.min() >= 0 and arr.max() <= 1)))
 
     @classmethod
     def from_device(cls, tensor: Any, *, name: str | None = None) -> Self:
@@ -145,7 +149,7 @@ class _CudaTensorBox(TensorLikeBox):
                 raise ValueError(f"Values of {point = } are invalid for {shape = }.")
             data[point] = 1
         data.setflags(write=False)
-        return cls._new(shape, host=data, name=name)
+        return cls._new(shape, host=data, name=name, binary=True)
 
     @classmethod
     def from_mapping(
@@ -200,6 +204,17 @@ class _CudaTensorBox(TensorLikeBox):
     @property
     def is_resident(self) -> bool:
         return self._dev is not None
+
+    def is_binary(self) -> bool:
+        """Whether every entry is 0 or 1 (a relation's indicator).  Whole-tree plans size their intermediates on
+        that assumption, so ``TreeContraction`` checks it for counting leaves; device-produced boxes are checked
+        by one kernel (``tsb_all_binary``), once."""
+        if self._binary is None:
+            from .. import _native
+
+            dev, _, _ = self._physical()
+            self._binary = _native.all_binary(dev)
+        return self._binary
 
     def _physical(self) -> tuple[Any, tuple[int, ...], tuple[int, ...]]:
         """``(flat device tensor, physical dims, axes)`` with ``logical = transpose(phys, axes)``."""
@@ -283,6 +298,7 @@ class _CudaTensorBox(TensorLikeBox):
                 host=None if self._host is None else np.transpose(self._host, out_ports),
                 dev=self._dev,
                 axes=tuple(axes[p] for p in out_ports),
+                binary=self._binary,
             )
             if new._dev is None:
                 new._axes = None
@@ -452,13 +468,13 @@ class CudaCountRel(_CudaTensorBox):
         if rel._host is not None:
             host = rel._host.astype(np.int64)
             host.setflags(write=False)
-            return cls._new(rel._dims, host=host, name=rel.name)
+            return cls._new(rel._dims, host=host, name=rel.name, binary=True)
         from .. import _native
 
         src = rel.device_tensor.reshape(-1)
         out = _native.empty(src.numel(), MODE_COUNT, like=src)
         _native.widen(src, out)
-        return cls._new(rel._dims, dev=out, name=rel.name)
+        return cls._new(rel._dims, dev=out, name=rel.name, binary=True)
 
 
 FinRel = CudaFinRel

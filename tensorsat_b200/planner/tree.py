@@ -210,10 +210,16 @@ class ContractionTree:
             if len(tree.sliced_wires) >= max_slices_log2:
                 raise ValueError("Slicing budget exhausted before reaching the target size.")
             w_max = tree.width()
+            lg = [math.log2(d) for d in self.network.size_dict]
             cands: set[int] = set()
             for st in tree.steps:
-                if len(st.out_wires) >= w_max - 1e-9:
+                if sum(lg[w] for w in st.out_wires) >= w_max - 1e-9:   # log2 size, any extents
                     cands |= st.out_wires
+            done = set(tree.sliced_wires)
+            for ws in self.network.inputs:   # a leaf can be the largest tensor left
+                rest = set(ws) - done
+                if sum(lg[w] for w in rest) >= w_max - 1e-9:
+                    cands |= rest
             cands -= out
             if not cands:
                 raise ValueError("No sliceable wire left in the largest intermediates.")

@@ -366,40 +366,112 @@ def test_contract2_validation_errors():
 
 
 # ------------------------------------------------------------------------------------ permutes
+def _resident(cls, arr):
+    """A box whose data lives ONLY on the device: a lazy ``rewire`` of it is materialised by the permute kernels
+    (FinRel._rewire's transpose view, tensorsat/lang/fin_rel.py:379-382, walked by the next consumer)."""
+    box = cls(arr)
+    box._physical()
+    box._host = None
+    return box
+
+
+def _permute_on_device(box, perm):
+    """``box.rewire(perm).device_tensor`` with proof that a permute kernel produced it."""
+    from tensorsat_b200 import _native
+
+    _native.trace(True)
+    before = _native.launch_count()
+    out = box.rewire(perm).device_tensor.cpu().numpy()
+    counts = _native.kernel_counts()
+    _native.trace(False)
+    assert _native.launch_count() > before
+    return out, counts
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_permute_random(seed):
     rng = np.random.default_rng(3000 + seed)
     r = int(rng.integers(9, SCALE["big_bits"] + 1))
     t = _rand01(rng, (2,) * r)
     perm = [int(p) for p in rng.permutation(r)]
-    box = CudaFinRel(t).rewire(perm)
-    assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm))
+    got, counts = _permute_on_device(_resident(CudaFinRel, t), perm)
+    assert np.array_equal(got, np.transpose(t, perm))
+    assert perm == sorted(perm) or any(k.startswith("k_permute") for k in counts), counts
 
 
 def test_permute_byte_transposes_in_registers():
     """Permutations that move the lowest axes away (4x4 byte-transpose kernel) incl. full reversal."""
     rng = np.random.default_rng(6)
+    seen = {}
     for r in (9, 12, 14, min(17, SCALE["big_bits"])):
         t = rng.integers(0, 2, size=(2,) * r, dtype=np.uint8)
+        box = _resident(CudaFinRel, t)
         perms = [list(range(r))[::-1], list(range(2, r)) + [0, 1], [r - 1, r - 2] + list(range(r - 2))]
         perms.append([int(p) for p in rng.permutation(r - 6)] + [r - 1, r - 2, r - 6, r - 5, r - 4, r - 3])
         for perm in perms:
-            box = CudaFinRel(t).rewire(perm)
-            assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm)), (r, perm)
+            got, counts = _permute_on_device(box, perm)
+            assert np.array_equal(got, np.transpose(t, perm)), (r, perm)
+            for k, v in counts.items():
+                seen[k] = seen.get(k, 0) + v
+    assert seen.get("k_permute_t4", 0) >= 4, seen
 
 
 def test_permute_keeps_low_axes_and_wide_elements():
     rng = np.random.default_rng(5)
     r = 13
     t = rng.integers(0, 1 << 40, size=(2,) * r, dtype=np.int64)
+    box = _resident(CudaCountRel, t)
     for perm in ([1, 0] + list(range(2, r)), list(range(r - 3, -1, -1)) + [r - 2, r - 1], list(range(r))[::-1]):
-        box = CudaCountRel(t).rewire(perm)
-        assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(t, perm))
+        got, counts = _permute_on_device(box, perm)
+        assert np.array_equal(got, np.transpose(t, perm))
+        assert any(k in counts for k in ("k_permute<8>", "k_permute<16>")), counts
     u = _rand01(rng, (2,) * 14)
+    ubox = _resident(CudaFinRel, u)
     for keep in (1, 2, 3, 4, 5):  # low axes left in place: gather groups of 2..16 bytes
         perm = [int(p) for p in rng.permutation(14 - keep)] + list(range(14 - keep, 14))
-        box = CudaFinRel(u).rewire(perm)
-        assert np.array_equal(box.device_tensor.cpu().numpy(), np.transpose(u, perm))
+        got, counts = _permute_on_device(ubox, perm)
+        assert np.array_equal(got, np.transpose(u, perm))
+        # (the random head may leave further low axes in place: the gather group is then wider)
+        assert any(f"k_permute<{g}>" in counts for g in (2, 4, 8, 16) if g >= min(16, 1 << keep)), (keep, counts)
+
+
+@pytest.mark.parametrize("elem_size,keep,kernel", [
+    (1, 0, "k_permute<1>"), (1, 1, "k_permute<2>"), (1, 2, "k_permute<4>"), (1, 3, "k_permute<8>"), (1, 4, "k_permute<16>"),
+    (4, 0, "k_permute<4>"), (4, 1, "k_permute<8>"), (4, 2, "k_permute<16>"),
+    (8, 0, "k_permute<8>"), (8, 1, "k_permute<16>"), (1, -1, "k_permute_t4"),
+])
+@pytest.mark.parametrize("rank", [14, 16])
+def test_permute_every_kernel_variant(elem_size, keep, kernel, rank):
+    """tsb_permute through the C-ABI on device buffers: every gather width of k_permute<G> (bytes the
+    permutation leaves contiguous, element size included), the 4x4 register-transpose kernel, element sizes
+    1 / 4 / 8, ranks >= 14 — each checked against np.transpose and against the kernel the library reports."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    if rank > SCALE["big_bits"] + 1:
+        pytest.skip("too large for the emulated build")
+    rng = np.random.default_rng(rank * 100 + elem_size * 10 + keep + 1)
+    dt = {1: np.uint8, 4: np.int32, 8: np.int64}[elem_size]
+    t = rng.integers(0, 200, size=(2,) * rank).astype(dt)
+    if keep < 0:      # no low axis stays, and the two lowest source axes leave the four lowest destination axes
+        head = [int(p) for p in rng.permutation(rank - 2)]
+        perm = head[:3] + [rank - 1, rank - 2] + head[3:]
+    else:
+        moved = rank - keep
+        while True:   # the lowest moved axis must really move (else one more byte group stays contiguous) ...
+            head = [int(p) for p in rng.permutation(moved)]
+            if head[-1] != moved - 1 and (elem_size > 1 or keep > 0 or moved - 1 in head[-4:] or moved - 2 in head[-4:]):
+                break  # ... and with nothing kept, byte tensors stay off the register-transpose variant
+        perm = head + list(range(moved, rank))
+    src = torch.from_numpy(t.reshape(-1).copy()).to(_native.device())
+    dst = torch.empty_like(src)
+    _native.trace(True)
+    _native.permute(src, dst, (2,) * rank, perm, elem_size)
+    counts = _native.kernel_counts()
+    _native.trace(False)
+    assert np.array_equal(dst.cpu().numpy().reshape((2,) * rank), np.transpose(t, perm)), perm
+    assert counts == {kernel: 1}, (perm, counts)
 
 
 # ------------------------------------------------------------------------------------ whole networks
@@ -705,6 +777,24 @@ def test_autoray_backend_functions():
     assert np.array_equal(ab.stack([B, B, B], 1).tensor, np.stack([b, b, b], 1))
     C = CudaCountRel(a)
     assert np.array_equal(ab.tensordot(C, C, axes=2).tensor, np.tensordot(a.astype(np.int64), a.astype(np.int64), axes=2))
+    # device-resident operands: transpose is lazy (like the reference's view) and is materialised on the device,
+    # by the permute kernel when read out, or folded into the operand's wire order when contracted
+    from tensorsat_b200 import _native
+
+    big = _rand01(rng, (2,) * 12)
+    perm = [int(p) for p in rng.permutation(12)]
+    G = _resident(CudaFinRel, big)
+    _native.trace(True)
+    T = ab.transpose(G, perm)
+    assert _native.kernel_counts() == {}
+    assert np.array_equal(T.device_tensor.cpu().numpy(), np.transpose(big, perm))
+    assert any(k.startswith("k_permute") for k in _native.kernel_counts())
+    T2 = ab.transpose(_resident(CudaFinRel, big), perm)
+    eq = "abcdefghijkl,lkjihg->abcdef"
+    want = np.sign(np.einsum(eq, np.transpose(big, perm).astype(np.int64), b.reshape(2, 2, 2, 1, 1, 1) * np.ones((2,) * 6, np.int64)))
+    got = ab.einsum(eq, T2, CudaFinRel((b.reshape(2, 2, 2, 1, 1, 1) * np.ones((2,) * 6, np.uint8)).astype(np.uint8)))
+    _native.trace(False)
+    assert np.array_equal(got.tensor, want.astype(np.uint8))
     with pytest.raises(TypeError):
         ab.shape(3)
     with pytest.raises(ValueError):
@@ -789,6 +879,58 @@ def test_contract_from_host_matches_device_leaves():
         assert bool(c.contract_from_host([a.tolist() for a in leaves])) == want
     with pytest.raises(ValueError):
         c.contract_from_host(leaves[:-1])
+
+
+def test_contract_from_host_with_repeated_output_wires():
+    """Repeated output wires (a diagonal of the result, simple.py:287-289): the host entry point returns the same
+    tensor as contract(), which rewires the plan's distinct-output result."""
+    from tensorsat_b200.diagrams import Wiring
+
+    rng = np.random.default_rng(11)
+    wiring = Wiring(wire_types=[FinSet(2)] * 4, slot_wires_list=[[0, 1], [1, 2, 3], [3, 0]], out_wires=[0, 0, 2])
+    leaves = [_rand01(rng, (2, 2), 0.7), _rand01(rng, (2, 2, 2), 0.7), _rand01(rng, (2, 2), 0.7)]
+    net = Network(((0, 1), (1, 2, 3), (3, 0)), (0, 2), (2, 2, 2, 2))
+    c = TreeContraction(CudaFinRel, wiring, ssa_path=[(0, 1), (3, 2)])
+    got = c.contract_from_host(leaves)
+    want2 = (np.einsum("ab,bcd,da->ac", *[x.astype(np.int64) for x in leaves]) > 0).astype(np.uint8)
+    want = np.zeros((2, 2, 2), np.uint8)
+    for a in range(2):
+        want[a, a, :] = want2[a, :]
+    assert got.shape == (2, 2, 2) and np.array_equal(got, want)
+    assert net.num_leaves == 3
+
+
+def test_weighted_counting_leaves_are_rejected_by_plans_and_exact_step_by_step():
+    """A plan stages its leaves as 0/1 bytes and sizes every intermediate from that bound: counting boxes with
+    other entries must not be truncated silently.  SimpleContraction (one contract2 per step, int64) is exact."""
+    import torch  # noqa: F401
+
+    from tensorsat_b200 import _native
+    from tensorsat_b200.diagrams import Diagram, Wiring
+
+    wiring = Wiring(wire_types=[FinSet(2)] * 3, slot_wires_list=[[0, 1], [1, 2]], out_wires=[0, 2])
+    a = np.array([[1, 2], [3, 300]], dtype=np.int64)
+    b = np.array([[5, 1], [4, 5]], dtype=np.int64)
+    boxes = (CudaCountRel(a), CudaCountRel(b))
+    assert not boxes[0].is_binary() and CudaCountRel(np.ones((2, 2), np.int64)).is_binary()
+    diagram = Diagram(wiring, boxes)
+    want = a @ b
+    got = SimpleContraction(CudaCountRel, wiring, [(0, 1)]).contract(diagram)
+    assert np.array_equal(got.tensor, want) and int(got.tensor[1, 1]) == 1503
+    with pytest.raises(ValueError, match="0/1"):
+        TreeContraction(CudaCountRel, wiring, ssa_path=[(0, 1)]).contract(diagram)
+    # a device-produced count tensor fed back as a leaf is checked on the device (tsb_all_binary)
+    fed = (got, CudaCountRel(np.ones((2, 2), np.int64)))
+    assert got._binary is None
+    with pytest.raises(ValueError, match="0/1"):
+        TreeContraction(CudaCountRel, wiring, ssa_path=[(0, 1)]).contract(Diagram(wiring, fed))
+    assert got._binary is False
+    ok = CudaCountRel.contract2(CudaCountRel(np.eye(2, dtype=np.int64)), [0, 1], CudaCountRel(np.eye(2, dtype=np.int64)), [1, 2], [0, 2])
+    assert ok._binary is None and ok.is_binary()
+    res = TreeContraction(CudaCountRel, wiring, ssa_path=[(0, 1)]).contract(Diagram(wiring, (ok, CudaCountRel(np.ones((2, 2), np.int64)))))
+    assert np.array_equal(res.tensor, np.ones((2, 2), np.int64))
+    assert _native.all_binary(_native.upload(np.array([0, 1, 1, 0], np.uint8)))
+    assert not _native.all_binary(_native.upload(np.array([0, 1, -1, 0], np.int64)))
 
 
 def test_slice_blocks_restrict_the_once_only_tensors():

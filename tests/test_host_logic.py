@@ -137,6 +137,18 @@ def test_tree_search_and_slicing():
         ContractionTree(net, ((0, 0),) + e.ssa_path[1:])
 
 
+def test_slice_to_on_non_binary_extents():
+    """slice_to compares log2 SIZES (not wire counts) when it picks the largest intermediates: a ring of four
+    extent-4 wires is sliceable to 2^2-entry intermediates."""
+    net = Network(((0, 1), (1, 2), (2, 3), (3, 0)), (), (4, 4, 4, 4))
+    tree = ContractionTree(net, [(0, 1), (2, 3), (4, 5)])
+    assert tree.width() == 4.0
+    sliced = tree.slice_to(2)
+    assert sliced.width() <= 2.0 and sliced.num_slices == 16
+    mixed = ContractionTree(Network(((0, 1), (1, 2), (2, 0)), (), (3, 2, 6)), [(0, 1), (3, 2)])
+    assert mixed.slice_to(2).width() <= 2.0
+
+
 def test_annealed_elimination_order_is_valid_and_never_worse():
     """The opt-in annealing of the order's tail (planner/search.py) is deterministic for a seed, returns a valid
     tree over the same network, and is kept only when the real objective improves."""
