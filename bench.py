@@ -169,6 +169,71 @@ def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22) -> dict:
                        f"extrapolated x{n / n_sample:.0f}")}
 
 
+def c4_subcube_leg(world: int, rank: int, keep: int, steps: int) -> dict | None:
+    """BASELINE config 4 (random 3-SAT n=200 m=852 seed 0, the north-star's sliced multi-GPU instance) on a SAMPLED
+    sub-cube: the tree (width 136) is sliced to 2^30-entry intermediates = 2^106 slices; all but `keep` sliced
+    wires are pinned along a committed model of the instance, the remaining 2^keep slices are split over the
+    ranks in contiguous blocks and combined by one all-reduce (max).  The sub-cube contains the model, so its
+    exact answer is SAT (checked)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tensorsat_b200 import _native
+    from tensorsat_b200.distributed import all_reduce_result, slice_block
+    from tensorsat_b200.planner import subcube
+
+    if not os.path.exists(subcube.path_of("c4")):
+        return None
+    f = subcube.load("c4")
+    sub, subleaves, asg = f.subcube(keep)
+    net = sub.network
+    plan = _native.Plan(net.inputs, net.output, net.size_dict, sub.ssa_path, sub.sliced_wires, mode=_native.MODE_SAT)
+    leaves = [_native.upload(np.ascontiguousarray(t, dtype=np.uint8)) for t in subleaves]
+    out = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
+    n = int(plan.info["n_slices"])
+    lo, hi = slice_block(n, rank, world)
+
+    def step() -> None:
+        plan.execute(leaves, out, lo, hi)
+        if world > 1:
+            all_reduce_result(out, _native.MODE_SAT)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    result = int(out.cpu().numpy().reshape(-1)[0])
+    info = plan.info
+    alg = info["alg_bytes_shared"] + info["alg_bytes_per_slice"] * n
+    res = {
+        "workload": (f"{f.description}; elimination-order tree (width {f.extra['tree_log2_width']:.0f}) sliced to 2^30-entry "
+                     f"intermediates = 2^{f.extra['n_sliced']} slices of the full instance; SAMPLED: {len(asg)} sliced wires pinned "
+                     f"along a committed model, the other 2^{keep} = {n} slices executed"),
+        "value": ms * 1e-3, "unit": "s", "ms_per_slice": ms / max(hi - lo, 1), "n_slices": n, "slices_per_rank": int(hi - lo),
+        "steps": steps, "scaling": "strong", "result": "SAT" if result else "UNSAT", "expected": "SAT (the sub-cube contains the model)",
+        "kernels_once": int(info["n_kernels_shared"]), "kernels_per_slice": int(info["n_kernels_per_slice"]),
+        "alg_bytes_moved_per_contraction": alg, "alg_GBps": alg / (ms * 1e-3) / 1e9,
+        "peak_arena_bytes": int(info["peak_bytes"]), "timing": "CUDA events per contraction incl. the all-reduce, max over ranks",
+    }
+    assert result == 1, "the sampled sub-cube of config 4 contains a model: the contraction must say SAT"
+    plan.close()
+    return res
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -201,6 +266,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pack", action="store_true", help="keep boolean intermediates at one byte per entry (A/B runs)")
     ap.add_argument("--batch-log2", type=int, default=None, help="override the plan's once-only size limit (experiments)")
+    ap.add_argument("--c4-keep", type=int, default=10, help="config-4 sub-cube leg: 2^keep slices (0 < keep; -1: skip the leg)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
@@ -303,6 +369,9 @@ def main() -> None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
     clocks = sampler.stop() if rank == 0 else None
+    desc_graph = plan.describe()
+    # ---- the north-star's sliced instance (config 4) on a sampled sub-cube, same ranks
+    c4 = c4_subcube_leg(world, rank, args.c4_keep, steps=3) if args.c4_keep > 0 else None
 
     # ---- per-kernel roofline: instrumented pass (CUDA events around every launch of the plan)
     roof = None
@@ -357,7 +426,9 @@ def main() -> None:
                        "peak_arena_bytes": int(plan.info["peak_bytes"]), "kernels_per_step": launches // max(args.steps, 1),
                        "alg_bytes_per_step": plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n_slices,
                        "alg_bytes_per_step_at_1B_per_entry": plan.info["alg_bytes_u8_shared"] + plan.info["alg_bytes_u8_per_slice"] * n_slices,
-                       "bit_packed_steps": int(plan.info["n_packed_steps"]), "conversions": int(plan.info["n_conversions"])},
+                       "bit_packed_steps": int(plan.info["n_packed_steps"]), "conversions": int(plan.info["n_conversions"]),
+                       "cuda_graph": {k: desc_graph[k] for k in ("graph_captures", "graph_replays")},
+                       "c4_subcube": c4},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": contraction.h2d_bytes,
                     "d2h_bytes_per_step": contraction.d2h_bytes},

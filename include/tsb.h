@@ -27,8 +27,9 @@
  *     (e.g. torch storage) unless obtained from the arena.  No torch types cross the ABI.
  *   - All work is enqueued on the caller-supplied stream (a cudaStream_t passed as
  *     void*); the only synchronising calls are tsb_all_ones and tsb_scalar_to_host.
- *   - A context is bound to one device and is not thread-safe; distinct contexts may be
- *     used concurrently (one per rank / process).
+ *   - A context is bound to one device.  Its arena is thread-safe and stream-aware; a plan
+ *     serialises its executions (an execution on another stream than the previous one waits
+ *     for it), so a context may be shared by the streams / threads of one process.
  *   - Wires are small non-negative integers < n_wires; wire_extents[w] is the dimension of
  *     wire w.  Power-of-two extents take the fast kernels, anything else a generic one.
  *   - mode TSB_SAT clamps every result to {0,1} (boolean semiring, count > 0);
@@ -83,11 +84,18 @@ typedef struct {
   size_t peak_in_use_bytes; /* high-water mark of in_use_bytes */
   size_t device_allocs;     /* number of cudaMalloc calls so far */
   size_t cache_hits;        /* allocations served without touching the driver */
+  size_t cross_stream_waits; /* cached blocks handed to another stream than their last user's (ordered by an event) */
 } tsb_arena_stats_t;
 
+/* The arena is stream-aware and thread-safe: a block released with tsb_arena_release_async remembers the stream
+ * its last user ran on (an event is recorded there), and an allocation for another stream is ordered after it.
+ * tsb_arena_alloc / tsb_arena_release are the stream-less forms: the caller guarantees that nothing using a
+ * block it releases is still in flight. */
 int tsb_arena_reserve(tsb_ctx* ctx, size_t bytes); /* pre-size from a plan's peak estimate */
 int tsb_arena_alloc(tsb_ctx* ctx, size_t bytes, void** ptr);
 int tsb_arena_release(tsb_ctx* ctx, void* ptr);
+int tsb_arena_alloc_async(tsb_ctx* ctx, size_t bytes, tsb_stream stream, void** ptr);
+int tsb_arena_release_async(tsb_ctx* ctx, void* ptr, tsb_stream stream);
 int tsb_arena_trim(tsb_ctx* ctx); /* return all cached blocks to the driver */
 int tsb_arena_stats(tsb_ctx* ctx, tsb_arena_stats_t* stats);
 
@@ -179,14 +187,19 @@ typedef struct {
   uint32_t flags;              /* TSB_PLAN_* */
 } tsb_plan_desc;
 
-#define TSB_PLAN_NO_GRAPH 1u     /* reserved: plans launch their kernels directly (overlap comes from programmatic
-                                    dependent launch); accepted and ignored */
+#define TSB_PLAN_NO_GRAPH 1u     /* never replay executions of this plan as a CUDA graph: every call launches its
+                                    kernels directly (the default captures the launch sequence on the second
+                                    execution with the same slice range / result buffer and replays it afterwards,
+                                    DESIGN.md 3.7) */
 #define TSB_PLAN_FORCE_GENERIC 2u /* use only the generic kernel (parity reference on device) */
 #define TSB_PLAN_NO_GEMM 4u      /* never lower a step to the tcgen05 GEMM */
 #define TSB_PLAN_NO_PACK 8u      /* keep every boolean intermediate at one byte per entry (no bit-packing) */
 #define TSB_PLAN_NO_FUSE 16u     /* one launch per tree step (no fused n-ary steps) */
 /* Environment knobs read by the library (A/B runs and tests; defaults in parentheses):
  *   TSB_PDL (1)              0: plain stream order instead of programmatic dependent launch
+ *   TSB_GRAPH (1)            0: no CUDA-graph replay of plan executions (same as TSB_PLAN_NO_GRAPH on every plan)
+ *   TSB_GRAPH_STREAMS (4)    side streams used while CAPTURING: the independent launches of a wave of the once-only
+ *                            schedule become parallel branches of the graph
  *   TSB_PACK_MIN_LOG2 (20)   steps touching a tensor of at least 2^x entries run bit-packed
  *   TSB_PACK_EXPAND_LOG2 (27) largest broadcast twin of a small operand, log2 entries
  *   TSB_PACK_GATHERED (1)    0: gathered per-slice results are stored as bytes even between packed steps

@@ -36,6 +36,7 @@ class ArenaStats(C.Structure):
         ("peak_in_use_bytes", C.c_size_t),
         ("device_allocs", C.c_size_t),
         ("cache_hits", C.c_size_t),
+        ("cross_stream_waits", C.c_size_t),
     ]
 
 
@@ -84,7 +85,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = [
     "tsb_version", "tsb_last_error", "tsb_ctx_create", "tsb_ctx_destroy", "tsb_ctx_launch_count", "tsb_ctx_trace", "tsb_ctx_trace_json",
-    "tsb_arena_reserve", "tsb_arena_alloc", "tsb_arena_release", "tsb_arena_trim", "tsb_arena_stats",
+    "tsb_arena_reserve", "tsb_arena_alloc", "tsb_arena_release", "tsb_arena_alloc_async", "tsb_arena_release_async", "tsb_arena_trim", "tsb_arena_stats",
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
     "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_all_binary", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
     "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",

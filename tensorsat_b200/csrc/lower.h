@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 
 #include "k_generic.cuh"
@@ -18,33 +19,58 @@ namespace tsb {
 // ---------------------------------------------------------------------------------------------
 // Context: device, caching arena, launch accounting
 // ---------------------------------------------------------------------------------------------
+// Caching device allocator (north-star item (d)).  Blocks are cached by size; a released block remembers the
+// stream its last user ran on and an event recorded at release, and a later allocation on a DIFFERENT stream
+// first makes that stream wait for the event, so the host-side release of a block whose kernels are still in
+// flight is safe whatever stream asks next.  A mutex guards the bookkeeping.
 struct Arena {
-  std::multimap<size_t, void*> free_blocks;  // size -> ptr
-  std::map<void*, size_t> live;              // handed out
-  std::map<void*, size_t> owned;             // every block obtained from the driver
+  struct FreeBlock {
+    void* ptr;
+    cudaStream_t stream;  // stream the block's last user was enqueued on
+    cudaEvent_t event;    // recorded on that stream at release (nullptr: nothing in flight / unknown)
+  };
+  std::multimap<size_t, FreeBlock> free_blocks;  // size -> block
+  std::map<void*, size_t> live;                  // handed out
+  std::map<void*, size_t> owned;                 // every block obtained from the driver
+  std::vector<cudaEvent_t> event_pool;
+  std::mutex mu;
   tsb_arena_stats_t st{};
 
   static size_t round_up(size_t n) {
     const size_t q = n < (size_t(1) << 20) ? 512 : (size_t(1) << 20);
     return n == 0 ? q : (n + q - 1) / q * q;
   }
-  void* alloc(size_t bytes) {
+  // `stream`: where the caller will use the block; kNoStream = the caller orders its own work (C-ABI callers)
+  static cudaStream_t no_stream() { return (cudaStream_t)(intptr_t)-1; }
+  void* alloc(size_t bytes, cudaStream_t stream = no_stream()) {
+    std::lock_guard<std::mutex> lock(mu);
     const size_t need = round_up(bytes);
     auto it = free_blocks.lower_bound(need);
     // reuse a cached block unless it would waste more than half of it
     if (it != free_blocks.end() && it->first <= need * 2 + (size_t(1) << 20)) {
-      void* p = it->second;
-      live[p] = it->first;
-      st.in_use_bytes += it->first;
+      FreeBlock b = it->second;
+      const size_t size = it->first;
       free_blocks.erase(it);
+      if (b.event) {
+        if (b.stream != stream) {
+          // the previous user's work may still be running on another stream: order this one after it
+          // (a caller that names no stream gets a host-side wait instead)
+          if (stream == no_stream()) cudaEventSynchronize(b.event);
+          else cudaStreamWaitEvent(stream, b.event, 0);
+          st.cross_stream_waits++;
+        }
+        event_pool.push_back(b.event);
+      }
+      live[b.ptr] = size;
+      st.in_use_bytes += size;
       st.cache_hits++;
       st.peak_in_use_bytes = std::max(st.peak_in_use_bytes, st.in_use_bytes);
-      return p;
+      return b.ptr;
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, need);
     if (e != cudaSuccess) {
-      trim();
+      trim_locked();
       e = cudaMalloc(&p, need);
     }
     if (e != cudaSuccess) {
@@ -60,22 +86,47 @@ struct Arena {
     st.peak_in_use_bytes = std::max(st.peak_in_use_bytes, st.in_use_bytes);
     return p;
   }
-  void release(void* p) {
+  // `stream`: where the block's last user was enqueued (an event is recorded there); no_stream(): the caller
+  // guarantees that nothing using the block is still in flight
+  void release(void* p, cudaStream_t stream = no_stream()) {
+    std::lock_guard<std::mutex> lock(mu);
     auto it = live.find(p);
     TSB_CHECK(it != live.end(), TSB_ERR_INVALID, "arena: release of a pointer the arena does not own");
+    FreeBlock b{p, stream, nullptr};
+    if (stream != no_stream()) {
+      if (event_pool.empty()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) event_pool.push_back(e);
+      }
+      if (!event_pool.empty()) {
+        b.event = event_pool.back();
+        event_pool.pop_back();
+        cudaEventRecord(b.event, stream);
+      }
+    }
     st.in_use_bytes -= it->second;
-    free_blocks.emplace(it->second, p);
+    free_blocks.emplace(it->second, b);
     live.erase(it);
   }
   void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    trim_locked();
+  }
+  void trim_locked() {
     for (auto& kv : free_blocks) {
-      cudaFree(kv.second);
+      if (kv.second.event) {
+        cudaEventSynchronize(kv.second.event);
+        event_pool.push_back(kv.second.event);
+      }
+      cudaFree(kv.second.ptr);
       st.reserved_bytes -= kv.first;
-      owned.erase(kv.second);
+      owned.erase(kv.second.ptr);
     }
     free_blocks.clear();
   }
   ~Arena() {
+    for (auto& kv : free_blocks) if (kv.second.event) cudaEventDestroy(kv.second.event);
+    for (auto e : event_pool) cudaEventDestroy(e);
     for (auto& kv : owned) cudaFree(kv.first);
   }
 };
@@ -83,6 +134,8 @@ struct Arena {
 }  // namespace tsb
 
 struct tsb_ctx {
+  int refs = 1;            // the creator's reference + one per live plan; freed when it drops to zero
+  bool gemm_attr_set = false;
   int device = 0;
   int sm_count = 148;
   int64_t launches = 0;
@@ -92,20 +145,35 @@ struct tsb_ctx {
   void note(const char* kernel) {
     launches++;
     if (trace) kcount[kernel]++;
+    if (cap_counts) (*cap_counts)[kernel]++;
   }
   tsb::Arena arena;
+  std::vector<void*>* hold = nullptr;              // set while a plan execution is captured into a CUDA graph
+  std::map<std::string, int64_t>* cap_counts = nullptr;  // per-kernel launches of the execution being captured
   int* d_flag = nullptr;  // scratch for all_ones
   uint8_t* d_one = nullptr;  // the u8 scalar 1
 };
 
 namespace tsb {
 
-// RAII temp buffer from the arena (released on scope exit; safe for stream-ordered reuse)
+void ctx_unref(tsb_ctx* ctx);  // tsb_ops.cu
+
+// RAII temp buffer from the arena for work enqueued on `stream`.  It is released on the host at scope exit while
+// its kernels may still be in flight: the arena orders any later user on another stream after them (event recorded
+// at release).  While a plan execution is being captured into a CUDA graph (ctx->hold != nullptr) the buffer is
+// handed to the graph's owner instead: a replay uses the same addresses, so the memory must stay the graph's.
 struct Temp {
   tsb_ctx* ctx;
+  cudaStream_t stream;
   void* p = nullptr;
-  Temp(tsb_ctx* c, size_t bytes) : ctx(c) { p = c->arena.alloc(bytes); }
-  ~Temp() { if (p) ctx->arena.release(p); }
+  Temp(tsb_ctx* c, size_t bytes, cudaStream_t s) : ctx(c), stream(s) {
+    p = c->arena.alloc(bytes, c->hold ? tsb::Arena::no_stream() : s);
+  }
+  ~Temp() {
+    if (!p) return;
+    if (ctx->hold) ctx->hold->push_back(p);
+    else ctx->arena.release(p, stream);
+  }
   Temp(const Temp&) = delete;
   Temp& operator=(const Temp&) = delete;
 };

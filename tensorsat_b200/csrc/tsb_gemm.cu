@@ -315,10 +315,9 @@ void gemm_u8_impl(tsb_ctx* ctx, const void* A, const void* B, void* C, int b_bit
   const size_t smem = 1024 + p.stages * stage_bytes + (2 * kGemmMaxStages + 4) * sizeof(uint64_t) + 16;
   CUtensorMap ma = make_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)Bt, (uint32_t)p.block_k, kGemmBlockM, swz);
   CUtensorMap mb = make_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)Bt, (uint32_t)p.block_k, (uint32_t)p.block_n, swz);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->gemm_attr_set) {   // per context, hence per device
     TSB_CUDA(cudaFuncSetAttribute(k_gemm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    ctx->gemm_attr_set = true;
   }
   const int grid = (int)std::min<int64_t>(p.num_tiles, ctx->sm_count);
   k_gemm_i8<<<grid, kGemmThreads, smem, stream>>>(ma, mb, p, C);

@@ -179,19 +179,19 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
         const BitLabels a_can = cat(g.B, g.M, g.K), b_can = cat(g.B, g.N, g.K), c_can = cat(g.B, g.M, g.N);
         std::unique_ptr<Temp> ta, tb, tc, tc2;
         if (ab != a_can) {
-          ta.reset(new Temp(ctx, (size_t)1 << ab.size()));
+          ta.reset(new Temp(ctx, (size_t)1 << ab.size(), stream));
           permute_bits(ctx, pa, ab, ta->p, a_can, 1, stream);
           pa = ta->p;
         }
         if (bb != b_can) {
-          tb.reset(new Temp(ctx, (size_t)1 << bb.size()));
+          tb.reset(new Temp(ctx, (size_t)1 << bb.size(), stream));
           permute_bits(ctx, pb, bb, tb->p, b_can, 1, stream);
           pb = tb->p;
         }
         const int gemm_dt = clamp ? TSB_U8 : TSB_I32;
         void* pc = out;
         if (c_can != ob || gemm_dt != dout) {
-          tc.reset(new Temp(ctx, (size_t)dtype_size(gemm_dt) << ob.size()));
+          tc.reset(new Temp(ctx, (size_t)dtype_size(gemm_dt) << ob.size(), stream));
           pc = tc->p;
         }
         gemm_u8_impl(ctx, pa, pb, pc, (int)g.B.size(), (int)g.M.size(), (int)g.N.size(), (int)g.K.size(), gemm_dt,
@@ -205,7 +205,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
               ctx->note("k_convert");
               return;
             }
-            tc2.reset(new Temp(ctx, (size_t)dtype_size(dout) << ob.size()));
+            tc2.reset(new Temp(ctx, (size_t)dtype_size(dout) << ob.size(), stream));
             TSB_LAUNCH(k_convert, dim3(grid_for(ctx, n_out, 256)), dim3(256), 0, stream, (const void*)src, gemm_dt,
                        tc2->p, dout, n_out, 0);
             ctx->note("k_convert");
@@ -230,7 +230,7 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
         tb.insert(tb.end(), ob.begin(), ob.end());
         if ((size_t)(clamp ? 1 : dtype_size(dout)) << std::min<size_t>(tb.size(), 40) <= ((size_t)1 << 34) && tb.size() <= 34) {
           const int tdt = clamp ? TSB_U8 : dout;
-          Temp tmp(ctx, (size_t)dtype_size(tdt) << tb.size());
+          Temp tmp(ctx, (size_t)dtype_size(tdt) << tb.size(), stream);
           // labels -> fresh wire ids for the recursive calls (one wire per bit label)
           std::map<int64_t, int32_t> id;
           auto wires_of = [&](const BitLabels& b) {
@@ -268,12 +268,12 @@ void contract2_impl(tsb_ctx* ctx, const void* lhs, int lhs_rank, const int32_t* 
         // summed labels shared by both operands must not interleave differently: they are handled by
         // per-label strides, so any order works.
         if (lc != lb) {
-          tl.reset(new Temp(ctx, (size_t)dtype_size(dl) << lb.size()));
+          tl.reset(new Temp(ctx, (size_t)dtype_size(dl) << lb.size(), stream));
           permute_bits(ctx, lhs, lb, tl->p, lc, dtype_size(dl), stream);
           pl = tl->p; lb = lc;
         }
         if (rc != rb) {
-          tr.reset(new Temp(ctx, (size_t)dtype_size(dr) << rb.size()));
+          tr.reset(new Temp(ctx, (size_t)dtype_size(dr) << rb.size(), stream));
           permute_bits(ctx, rhs, rb, tr->p, rc, dtype_size(dr), stream);
           pr = tr->p; rb = rc;
         }
@@ -348,6 +348,12 @@ void rewire_impl(tsb_ctx* ctx, const void* src, int src_rank, const int32_t* sex
   launch_generic(ctx, g, sp, nullptr, dst, stream);
 }
 
+void ctx_unref(tsb_ctx* ctx) {
+  if (!ctx || --ctx->refs > 0) return;
+  if (ctx->d_flag) cudaFree(ctx->d_flag);
+  delete ctx;
+}
+
 }  // namespace tsb
 
 using namespace tsb;
@@ -374,10 +380,7 @@ int tsb_ctx_create(int device, tsb_ctx** ctx) {
 
 int tsb_ctx_destroy(tsb_ctx* ctx) {
   TSB_API_BEGIN
-  if (ctx) {
-    if (ctx->d_flag) cudaFree(ctx->d_flag);
-    delete ctx;
-  }
+  tsb::ctx_unref(ctx);   // freed once the plans created from it are gone too
   TSB_API_END
 }
 
@@ -429,6 +432,19 @@ int tsb_arena_release(tsb_ctx* ctx, void* ptr) {
   TSB_API_BEGIN
   check_ctx(ctx);
   ctx->arena.release(ptr);
+  TSB_API_END
+}
+int tsb_arena_alloc_async(tsb_ctx* ctx, size_t bytes, tsb_stream stream, void** ptr) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  TSB_CHECK(ptr != nullptr, TSB_ERR_INVALID, "null output pointer");
+  *ptr = ctx->arena.alloc(bytes, (cudaStream_t)stream);
+  TSB_API_END
+}
+int tsb_arena_release_async(tsb_ctx* ctx, void* ptr, tsb_stream stream) {
+  TSB_API_BEGIN
+  check_ctx(ctx);
+  ctx->arena.release(ptr, (cudaStream_t)stream);
   TSB_API_END
 }
 int tsb_arena_trim(tsb_ctx* ctx) {

@@ -15,7 +15,9 @@
 //  * per-tensor dtype in counting mode from a magnitude bound (u8 -> i32 -> i64).
 #include <cmath>
 #include <functional>
+#include <mutex>
 #include <sstream>
+#include <tuple>
 
 #include "lower.h"
 
@@ -149,6 +151,36 @@ struct tsb_plan {
   std::vector<void*> h_ptrs;           // host copy of the table (pageable: the async copy stages it)
   bool mask_root = false;              // root keeps the sliced wires; a final masked sum selects the executed slices
   int64_t mask_offset = -1;            // arena offset of the slice mask (u8, one entry per slice combination)
+  std::vector<void*> h_ptrs_uploaded;  // what d_ptrs holds (the upload is skipped when nothing changed)
+  // ---- executions are serialised: one at a time per plan, and one on another stream waits for the previous one
+  std::mutex mu;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  cudaEvent_t done_ev = nullptr;
+  // ---- CUDA-graph replay: the launch sequence of an execution is static per (slice range, result
+  // buffer); from the second execution with the same key on, it is captured once and replayed with one host call
+  struct GraphKey {
+    void* out; int64_t begin, end; uint64_t leaf_hash;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(out, begin, end, leaf_hash) < std::tie(o.out, o.begin, o.end, o.leaf_hash);
+    }
+  };
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<void*> held;                   // temporaries of the captured launches (owned until the graph dies)
+    std::map<std::string, int64_t> kcount;     // kernels per replay
+    int64_t launches = 0;
+    int rr_launches = 0;
+    uint64_t last_used = 0;
+  };
+  std::map<GraphKey, GraphEntry> graphs;
+  std::map<GraphKey, int> seen;          // executions per key so far (capture on the second)
+  std::set<GraphKey> ungraphable;        // capture failed once: always direct
+  void* gblock = nullptr;                // arena block owned by the graphs of this plan (same addresses on replay)
+  void* gres = nullptr;                  // small results land here inside a graph, then one D2D copy to the caller
+  uint64_t tick = 0;
+  int64_t n_replays = 0, n_captures = 0;
+  bool bakes_leaf_ptrs = false;          // some launch takes a leaf pointer as a kernel argument (not via d_ptrs)
 };
 
 namespace {
@@ -959,6 +991,9 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     if (op.kind == OP_STEP) mx = std::max(mx, ilog2(std::max<int64_t>(1, prod_ext(op.ow, P.wext))));
   }
   P.info.log2_max_tensor = mx;
+  for (auto& op : P.ops)
+    if (op.kind == OP_LEAF && !op.small) P.bakes_leaf_ptrs = true;
+  if (P.n_leaves == 1) P.bakes_leaf_ptrs = true;
 }
 
 // digits of a slice id (first sliced wire most significant)
@@ -1167,6 +1202,7 @@ int tsb_plan_create(tsb_ctx* ctx, const tsb_plan_desc* desc, tsb_plan** plan) {
     std::unique_ptr<tsb_plan> P(new tsb_plan());
     P->ctx = ctx;
     build_plan(*P, *desc);
+    ctx->refs++;   // a plan keeps its context alive (it returns arena blocks to it when destroyed)
     *plan = P.release();
     return TSB_OK;
   } catch (const tsb::Error& e) {
@@ -1197,7 +1233,8 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
   if (!plan || !needed) { tsb::set_error("null argument"); return TSB_ERR_INVALID; }
   std::ostringstream os;
   os << "{\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices
-     << ",\"restricted_launches\":" << plan->rr_launches << ",\"ops\":[";
+     << ",\"restricted_launches\":" << plan->rr_launches << ",\"graph_captures\":" << plan->n_captures
+     << ",\"graph_replays\":" << plan->n_replays << ",\"ops\":[";
   bool first = true;
   for (auto& op : plan->ops) {
     if (!first) os << ",";
@@ -1246,6 +1283,339 @@ int tsb_plan_timing_json(tsb_plan* plan, char* buf, size_t cap, size_t* needed) 
   return tsb_plan_describe(plan, buf, cap, needed);
 }
 
+}  // extern "C"
+
+namespace {
+
+// the slice mask of a masked root as a range of ones, when it is one (it is whenever the root's leading axes are
+// all the sliced wires in slice-id order, i.e. always unless a sliced wire touches no tensor)
+struct MaskPlan {
+  std::vector<uint8_t> host;   // full mask (fallback: uploaded from the host, direct executions only)
+  int64_t lo = 0, hi = 0;      // ones at [lo, hi)
+  bool is_range = false;
+};
+
+MaskPlan make_mask(const tsb_plan& P, int64_t slice_begin, int64_t slice_end) {
+  MaskPlan m;
+  if (!P.mask_root) return m;
+  const PNode& r = P.nodes[P.root];
+  m.host.assign((size_t)r.s_numel, 0);
+  for (int64_t sid = slice_begin; sid < slice_end; sid++) {
+    const std::vector<int64_t> digits = slice_digits(P, sid);
+    m.host[(size_t)(shared_offset(P, r, digits) / r.reg_numel)] = 1;
+  }
+  int64_t lo = 0, hi = (int64_t)m.host.size();
+  while (lo < hi && !m.host[(size_t)lo]) lo++;
+  while (hi > lo && !m.host[(size_t)hi - 1]) hi--;
+  m.is_range = true;
+  for (int64_t i = lo; i < hi; i++) m.is_range = m.is_range && m.host[(size_t)i];
+  m.lo = lo; m.hi = hi;
+  return m;
+}
+
+// Enqueues one whole execution on `stream`: [once-only schedule][slice loop][tail schedule][combine].  Everything it
+// launches depends only on (plan, base, out, slice range) — and on the leaf pointers where P.bakes_leaf_ptrs — so
+// the same call can run directly or under stream capture.  The pointer table d_ptrs is uploaded by the caller.
+void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs, int64_t slice_begin, int64_t slice_end,
+                       void* out, const MaskPlan& mask, cudaStream_t stream, bool timing, int n_side_max) {
+  tsb_ctx* ctx = P.ctx;
+  if (timing && P.ev.size() < 2 * P.ops.size() + 2) {
+    size_t old = P.ev.size();
+    P.ev.resize(2 * P.ops.size() + 2);
+    for (size_t i = old; i < P.ev.size(); i++) TSB_CUDA(cudaEventCreate(&P.ev[i]));
+  }
+  for (auto& op : P.ops) op.last_ms = 0;
+  auto timed = [&](size_t i, const std::function<void()>& f) {
+    if (timing) TSB_CUDA(cudaEventRecord(P.ev[2 * i], stream));
+    f();
+    if (timing) {
+      TSB_CUDA(cudaEventRecord(P.ev[2 * i + 1], stream));
+      TSB_CUDA(cudaEventSynchronize(P.ev[2 * i + 1]));
+      float ms = 0;
+      TSB_CUDA(cudaEventElapsedTime(&ms, P.ev[2 * i], P.ev[2 * i + 1]));
+      P.ops[i].last_ms += ms;
+    }
+  };
+  if (P.stack_out) {
+    const PNode& r = P.nodes[P.rnode];
+    TSB_CUDA(cudaMemsetAsync(base + r.offset, 0, r.bytes, stream));
+  }
+  for (int g : P.gathered_nodes) TSB_CUDA(cudaMemsetAsync(base + P.nodes[g].offset, 0, P.nodes[g].bytes, stream));
+  // An op may run on a side stream when its launch needs nothing but its descriptor and the arena block: packed
+  // steps, conversions and aligned byte merges (the other paths take temporaries from the stream-ordered arena).
+  auto forkable = [&](const Launch& l) {
+    if (l.op < 0) return false;
+    const POp& op = P.ops[l.op];
+    if (op.kind == OP_LEAF || P.nodes[op.out].is_out) return false;
+    if (op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND) return true;
+    if (op.kind != OP_STEP) return false;
+    if (op.use_bits) return true;
+    if (!op.use_merge || op.use_gemm) return false;
+    const PNode& a = P.nodes[op.lhs];
+    const PNode& b = P.nodes[op.rhs];
+    const PNode& o = P.nodes[op.out];
+    const uintptr_t al = ((uintptr_t)dtype_size(a.dtype) << __builtin_popcount((unsigned)op.md.nibL)) - 1;
+    const uintptr_t ar = ((uintptr_t)dtype_size(b.dtype) << __builtin_popcount((unsigned)op.md.nibR)) - 1;
+    return !a.is_out && !b.is_out && ((uintptr_t)a.offset & al) == 0 && ((uintptr_t)b.offset & ar) == 0 &&
+           ((uintptr_t)o.offset & 15) == 0 && P.rr_nfixed == 0;
+  };
+  auto run_one = [&](Launch& l, cudaStream_t st) {
+    l.last_ms = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (timing) {
+      TSB_CUDA(cudaEventCreate(&t0));
+      TSB_CUDA(cudaEventCreate(&t1));
+      TSB_CUDA(cudaEventRecord(t0, st));
+    }
+    if (l.op < 0) {
+      const int n = l.batch_end - l.batch_begin;
+      if (l.chain)
+        TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, st,
+                       (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
+      else
+        TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, st,
+                       (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
+      ctx->note(l.chain ? "k_small_chain" : "k_small_batch");
+      TSB_CUDA(cudaGetLastError());
+    } else {
+      POp& op = P.ops[l.op];
+      if (op.kind == OP_LEAF) {
+        if (!(P.n_leaves == 1 && !P.sliced.empty())) run_leaf(P, op, base, leaf_ptrs[op.leaf], out, st);
+      } else {
+        run_step(P, op, base, out, nullptr, false, st);
+      }
+    }
+    if (timing) {
+      TSB_CUDA(cudaEventRecord(t1, st));
+      TSB_CUDA(cudaEventSynchronize(t1));
+      float ms = 0;
+      TSB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+      l.last_ms = ms;
+      if (l.op >= 0) P.ops[l.op].last_ms = ms;
+      cudaEventDestroy(t0);
+      cudaEventDestroy(t1);
+    }
+  };
+  // once-only parts: waves of independent ops (small ops of a wave = one launch; the other launches of a wave are
+  // spread over the caller's stream and a few side streams, joined before the next wave — under capture this
+  // becomes parallel branches of the graph at no host cost per replay)
+  auto run_schedule = [&](std::vector<Launch>& sched) {
+    size_t li = 0;
+    while (li < sched.size()) {
+      size_t lj = li;
+      if (!timing && n_side_max > 0 && forkable(sched[li]))
+        while (lj < sched.size() && sched[lj].wave == sched[li].wave && forkable(sched[lj])) lj++;
+      const int group = (int)(lj - li);
+      if (group < 3) {
+        run_one(sched[li], stream);
+        li++;
+        continue;
+      }
+      const int n_side = std::min(n_side_max, group - 1);
+      while ((int)P.side.size() < n_side) {
+        cudaStream_t st;
+        TSB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        P.side.push_back(st);
+      }
+      while ((int)P.side_ev.size() < 1 + n_side) {
+        cudaEvent_t e;
+        TSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        P.side_ev.push_back(e);
+      }
+      TSB_CUDA(cudaEventRecord(P.side_ev[0], stream));
+      for (int q = 0; q < n_side; q++) TSB_CUDA(cudaStreamWaitEvent(P.side[q], P.side_ev[0], 0));
+      for (int g = 0; g < group; g++) {
+        const int lane = g % (n_side + 1);
+        run_one(sched[li + g], lane == 0 ? stream : P.side[lane - 1]);
+      }
+      for (int q = 0; q < n_side; q++) {
+        TSB_CUDA(cudaEventRecord(P.side_ev[1 + q], P.side[q]));
+        TSB_CUDA(cudaStreamWaitEvent(stream, P.side_ev[1 + q], 0));
+      }
+      li = lj;
+    }
+  };
+  // A rank that executes an aligned power-of-two block of slice ids computes only its own sub-blocks of the
+  // once-only tensors that keep sliced wires (run_step / pre_block); everything else is replicated.
+  P.rr_nfixed = 0;
+  P.rr_launches = 0;
+  {
+    static const bool restrict_pre = [] { const char* e = getenv("TSB_PRE_RESTRICT"); return !(e && e[0] == '0'); }();
+    const int64_t n = slice_end - slice_begin, total = P.info.n_slices;
+    bool binary = !P.sliced.empty();
+    for (auto w : P.sliced) binary = binary && P.wext[w] == 2;
+    if (restrict_pre && binary && n > 0 && n < total && (n & (n - 1)) == 0 && slice_begin % n == 0) {
+      P.rr_nfixed = (int)P.sliced.size() - ilog2(n);
+      P.rr_digits = slice_digits(P, slice_begin);
+    }
+  }
+  run_schedule(P.schedule);
+  P.rr_nfixed = 0;
+  // per-slice part
+  if (!P.sliced.empty()) {
+    for (int64_t sid = slice_begin; sid < slice_end; sid++) {
+      const std::vector<int64_t> digits = slice_digits(P, sid);
+      if (P.n_leaves == 1) {
+        // single tensor network with sliced wires: index the leaf, accumulate into the stacked buffer
+        const auto& lw = P.leaf_wires[0];
+        std::vector<int32_t> ext(lw.size()), fixed(lw.size(), -1), ports;
+        for (size_t q = 0; q < lw.size(); q++) {
+          ext[q] = P.wext[lw[q]];
+          for (size_t z = 0; z < P.sliced.size(); z++)
+            if (P.sliced[z] == lw[q]) fixed[q] = (int32_t)digits[z];
+        }
+        const PNode& r = P.nodes[P.rnode];
+        for (auto w : r.reg)
+          for (size_t q = 0; q < lw.size(); q++) if (lw[q] == w) { ports.push_back((int32_t)q); break; }
+        void* po = base + r.offset + shared_offset(P, r, digits) * dtype_size(r.dtype);
+        rewire_impl(ctx, leaf_ptrs[0], (int)lw.size(), ext.data(), fixed.data(), TSB_U8, po, (int)ports.size(),
+                    ports.data(), r.dtype, P.mode == TSB_SAT, true, stream);
+        continue;
+      }
+      for (int i : P.slice_ops) {
+        POp& op = P.ops[i];
+        timed((size_t)i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, stream); });
+      }
+    }
+  }
+  run_schedule(P.post_schedule);
+  if (P.mask_root) {
+    // out[o] = sum over sliced-wire combinations s in [slice_begin, slice_end) of root[s, o]
+    const PNode& r = P.nodes[P.root];
+    uint8_t* d_mask = base + P.mask_offset;
+    if (mask.is_range) {
+      TSB_CUDA(cudaMemsetAsync(d_mask, 0, mask.host.size(), stream));
+      if (mask.hi > mask.lo) TSB_CUDA(cudaMemsetAsync(d_mask + mask.lo, 1, (size_t)(mask.hi - mask.lo), stream));
+    } else {
+      TSB_CUDA(cudaMemcpyAsync(d_mask, mask.host.data(), mask.host.size(), cudaMemcpyHostToDevice, stream));
+    }
+    const std::vector<int32_t> rw = r.stored();
+    contract2_impl(ctx, base + r.offset, (int)rw.size(), rw.data(), r.dtype, d_mask, (int)r.slab.size(), r.slab.data(),
+                   TSB_U8, out, (int)r.reg.size(), r.reg.data(), P.info.out_dtype, P.n_wires, P.wext.data(), P.mode, false,
+                   false, stream);
+  }
+  if (P.stack_out) {
+    // [sliced output wires][other output wires] -> requested output order
+    const PNode& r = P.nodes[P.rnode];
+    std::vector<int32_t> axes = r.stored(), ext(axes.size()), ports;
+    for (size_t q = 0; q < axes.size(); q++) ext[q] = P.wext[axes[q]];
+    for (auto w : P.out_wires)
+      for (size_t q = 0; q < axes.size(); q++) if (axes[q] == w) { ports.push_back((int32_t)q); break; }
+    rewire_impl(ctx, base + r.offset, (int)axes.size(), ext.data(), nullptr, r.dtype, out, (int)ports.size(),
+                ports.data(), r.dtype, false, false, stream);
+  }
+}
+
+// pointer table for the batched small ops: [arena, out, leaves...]; uploaded only when it changed
+void upload_ptrs(tsb_plan& P, uint8_t* base, void* out, const void* const* leaf_ptrs, cudaStream_t stream) {
+  if (P.small_ops.empty()) return;
+  P.h_ptrs[0] = base;
+  P.h_ptrs[1] = out;
+  for (int i = 0; i < P.n_leaves; i++) P.h_ptrs[2 + i] = const_cast<void*>(leaf_ptrs[i]);
+  if (P.h_ptrs_uploaded == P.h_ptrs) return;
+  // pageable source: the runtime stages it before returning, so h_ptrs may change right after
+  TSB_CUDA(cudaMemcpyAsync(P.d_ptrs, P.h_ptrs.data(), (size_t)(P.n_leaves + 2) * sizeof(void*), cudaMemcpyHostToDevice,
+                           stream));
+  P.h_ptrs_uploaded = P.h_ptrs;
+}
+
+#ifndef TSB_HOST_EMU
+void destroy_graph_entry(tsb_plan& P, tsb_plan::GraphEntry& e) {
+  if (e.exec) cudaGraphExecDestroy(e.exec);
+  for (void* p : e.held) P.ctx->arena.release(p);
+  e.held.clear();
+  e.exec = nullptr;
+}
+
+constexpr size_t kGraphSmallResult = 64 * 1024;  // results up to this size go through the plan's own buffer
+constexpr size_t kGraphCacheEntries = 8;
+
+// Replays (capturing first, on the second execution with the same key) the execution as a CUDA graph.
+// Returns false when this call must run directly.
+bool execute_as_graph(tsb_plan& P, const void* const* leaf_ptrs, int64_t slice_begin, int64_t slice_end, void* out,
+                      const MaskPlan& mask, cudaStream_t stream) {
+  static const bool enabled = [] { const char* e = getenv("TSB_GRAPH"); return !(e && e[0] == '0'); }();
+  static const int graph_streams = [] { const char* e = getenv("TSB_GRAPH_STREAMS"); return e ? atoi(e) : 4; }();
+  tsb_ctx* ctx = P.ctx;
+  if (!enabled || (P.flags & TSB_PLAN_NO_GRAPH) || P.timing) return false;
+  if (P.mask_root && !mask.is_range) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+  const size_t out_bytes = (size_t)P.info.out_numel * dtype_size(P.info.out_dtype);
+  const bool own_result = out_bytes <= kGraphSmallResult;
+  tsb_plan::GraphKey key{own_result ? nullptr : out, slice_begin, slice_end, 0};
+  if (P.bakes_leaf_ptrs) {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < P.n_leaves; i++) h = (h ^ (uint64_t)(uintptr_t)leaf_ptrs[i]) * 1099511628211ull;
+    key.leaf_hash = h;
+  }
+  if (P.ungraphable.count(key)) return false;
+  auto it = P.graphs.find(key);
+  if (it == P.graphs.end()) {
+    if (P.seen[key]++ < 1) return false;  // first execution: direct (also warms the arena and the module)
+    // ---- capture
+    if (!P.gblock) P.gblock = ctx->arena.alloc((size_t)std::max<int64_t>(P.info.peak_bytes, 256));
+    if (own_result && !P.gres) P.gres = ctx->arena.alloc(std::max<size_t>(out_bytes, 256));
+    if (P.graphs.size() >= kGraphCacheEntries) {  // evict the least recently used entry
+      auto victim = P.graphs.begin();
+      for (auto q = P.graphs.begin(); q != P.graphs.end(); ++q)
+        if (q->second.last_used < victim->second.last_used) victim = q;
+      if (P.has_last) cudaStreamSynchronize(P.last_stream);
+      destroy_graph_entry(P, victim->second);
+      P.graphs.erase(victim);
+    }
+    tsb_plan::GraphEntry e;
+    const int64_t launches0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      ctx->hold = &e.held;
+      ctx->cap_counts = &e.kcount;
+      try {
+        enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, own_result ? P.gres : out, mask, stream,
+                          false, graph_streams);
+      } catch (const tsb::Error&) {
+        ok = false;
+      }
+      ctx->hold = nullptr;
+      ctx->cap_counts = nullptr;
+      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr) ok = false;
+    }
+    if (ok && cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    // the captured launches did not run: they are counted per replay
+    e.launches = ctx->launches - launches0;
+    ctx->launches = launches0;
+    if (ctx->trace)
+      for (auto& kv : e.kcount) ctx->kcount[kv.first] -= kv.second;
+    e.rr_launches = P.rr_launches;
+    if (!ok) {
+      (void)cudaGetLastError();
+      destroy_graph_entry(P, e);
+      P.ungraphable.insert(key);
+      return false;
+    }
+    P.n_captures++;
+    it = P.graphs.emplace(key, std::move(e)).first;
+  }
+  tsb_plan::GraphEntry& e = it->second;
+  e.last_used = ++P.tick;
+  upload_ptrs(P, (uint8_t*)P.gblock, own_result ? P.gres : out, leaf_ptrs, stream);
+  TSB_CUDA(cudaGraphLaunch(e.exec, stream));
+  if (own_result) TSB_CUDA(cudaMemcpyAsync(out, P.gres, out_bytes, cudaMemcpyDeviceToDevice, stream));
+  ctx->launches += e.launches;
+  if (ctx->trace)
+    for (auto& kv : e.kcount) ctx->kcount[kv.first] += kv.second;
+  P.rr_launches = e.rr_launches;
+  P.n_replays++;
+  return true;
+}
+#endif
+
+}  // namespace
+
+extern "C" {
+
 int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice_begin, int64_t slice_end, void* out,
                      tsb_stream stream_) {
   try {
@@ -1261,203 +1631,46 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       TSB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.info.out_numel * es, stream));
       return TSB_OK;
     }
-    Temp block(ctx, (size_t)std::max<int64_t>(P.info.peak_bytes, 256));
-    uint8_t* base = (uint8_t*)block.p;
-    const bool timing = P.timing;
-    if (timing && P.ev.size() < 2 * P.ops.size() + 2) {
-      size_t old = P.ev.size();
-      P.ev.resize(2 * P.ops.size() + 2);
-      for (size_t i = old; i < P.ev.size(); i++) TSB_CUDA(cudaEventCreate(&P.ev[i]));
+    // one execution at a time (the pointer table, the slice-range restriction and the graphs' arena block are
+    // per-plan state); an execution on another stream than the previous one is ordered after it
+    std::lock_guard<std::mutex> lock(P.mu);
+    if (!P.done_ev) TSB_CUDA(cudaEventCreateWithFlags(&P.done_ev, cudaEventDisableTiming));
+    if (P.has_last && P.last_stream != stream) TSB_CUDA(cudaStreamWaitEvent(stream, P.done_ev, 0));
+    auto mark_done = [&] {
+      TSB_CUDA(cudaEventRecord(P.done_ev, stream));
+      P.last_stream = stream;
+      P.has_last = true;
+    };
+    const MaskPlan mask = make_mask(P, slice_begin, slice_end);
+#ifndef TSB_HOST_EMU
+    if (execute_as_graph(P, leaf_ptrs, slice_begin, slice_end, out, mask, stream)) {
+      mark_done();
+      return TSB_OK;
     }
-    for (auto& op : P.ops) op.last_ms = 0;
-    auto timed = [&](size_t i, const std::function<void()>& f) {
-      if (timing) TSB_CUDA(cudaEventRecord(P.ev[2 * i], stream));
-      f();
-      if (timing) {
-        TSB_CUDA(cudaEventRecord(P.ev[2 * i + 1], stream));
-        TSB_CUDA(cudaEventSynchronize(P.ev[2 * i + 1]));
-        float ms = 0;
-        TSB_CUDA(cudaEventElapsedTime(&ms, P.ev[2 * i], P.ev[2 * i + 1]));
-        P.ops[i].last_ms += ms;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool outer_capture = cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (outer_capture) {
+      // the caller is capturing this stream into its own graph: the launches must keep their memory for as long
+      // as the plan lives (the caller's replays use the same addresses), and no event may be recorded
+      if (!P.gblock) P.gblock = ctx->arena.alloc((size_t)std::max<int64_t>(P.info.peak_bytes, 256));
+      static std::vector<void*> forever;   // temporaries of caller-captured launches are never recycled
+      ctx->hold = &forever;
+      try {
+        upload_ptrs(P, (uint8_t*)P.gblock, out, leaf_ptrs, stream);
+        enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, out, mask, stream, false, 0);
+      } catch (...) {
+        ctx->hold = nullptr;
+        throw;
       }
-    };
-    if (P.stack_out) {
-      const PNode& r = P.nodes[P.rnode];
-      TSB_CUDA(cudaMemsetAsync(base + r.offset, 0, r.bytes, stream));
+      ctx->hold = nullptr;
+      return TSB_OK;
     }
-    // pointer table for the batched small ops: [arena, out, leaves...]
-    if (!P.small_ops.empty()) {
-      P.h_ptrs[0] = base;
-      P.h_ptrs[1] = out;
-      for (int i = 0; i < P.n_leaves; i++) P.h_ptrs[2 + i] = const_cast<void*>(leaf_ptrs[i]);
-      TSB_CUDA(cudaMemcpyAsync(P.d_ptrs, P.h_ptrs.data(), (size_t)(P.n_leaves + 2) * sizeof(void*), cudaMemcpyHostToDevice,
-                               stream));
-    }
-    for (int g : P.gathered_nodes) TSB_CUDA(cudaMemsetAsync(base + P.nodes[g].offset, 0, P.nodes[g].bytes, stream));
-    // once-only parts: waves of independent ops (small ops of a wave = one launch)
-    // An op may run on a side stream when its launch needs nothing but its descriptor and the arena block: packed
-    // steps, conversions and aligned byte merges (the other paths take temporaries from the stream-ordered arena).
-    auto forkable = [&](const Launch& l) {
-      if (l.op < 0) return false;
-      const POp& op = P.ops[l.op];
-      if (op.kind == OP_LEAF || P.nodes[op.out].is_out) return false;
-      if (op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND) return true;
-      if (op.kind != OP_STEP) return false;
-      if (op.use_bits) return true;
-      if (!op.use_merge || op.use_gemm) return false;
-      const PNode& a = P.nodes[op.lhs];
-      const PNode& b = P.nodes[op.rhs];
-      const PNode& o = P.nodes[op.out];
-      const uintptr_t al = ((uintptr_t)dtype_size(a.dtype) << __builtin_popcount((unsigned)op.md.nibL)) - 1;
-      const uintptr_t ar = ((uintptr_t)dtype_size(b.dtype) << __builtin_popcount((unsigned)op.md.nibR)) - 1;
-      return !a.is_out && !b.is_out && ((uintptr_t)a.offset & al) == 0 && ((uintptr_t)b.offset & ar) == 0 &&
-             ((uintptr_t)o.offset & 15) == 0 && P.rr_nfixed == 0;
-    };
+#endif
     static const int n_side_max = [] { const char* e = getenv("TSB_WAVE_STREAMS"); return e ? atoi(e) : 0; }();
-    auto run_one = [&](Launch& l, cudaStream_t st) {
-      l.last_ms = 0;
-      cudaEvent_t t0 = nullptr, t1 = nullptr;
-      if (timing) {
-        TSB_CUDA(cudaEventCreate(&t0));
-        TSB_CUDA(cudaEventCreate(&t1));
-        TSB_CUDA(cudaEventRecord(t0, st));
-      }
-      if (l.op < 0) {
-        const int n = l.batch_end - l.batch_begin;
-        if (l.chain)
-          TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, st,
-                         (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
-        else
-          TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, st,
-                         (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
-        ctx->note(l.chain ? "k_small_chain" : "k_small_batch");
-        TSB_CUDA(cudaGetLastError());
-      } else {
-        POp& op = P.ops[l.op];
-        if (op.kind == OP_LEAF) {
-          if (!(P.n_leaves == 1 && !P.sliced.empty())) run_leaf(P, op, base, leaf_ptrs[op.leaf], out, st);
-        } else {
-          run_step(P, op, base, out, nullptr, false, st);
-        }
-      }
-      if (timing) {
-        TSB_CUDA(cudaEventRecord(t1, st));
-        TSB_CUDA(cudaEventSynchronize(t1));
-        float ms = 0;
-        TSB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-        l.last_ms = ms;
-        if (l.op >= 0) P.ops[l.op].last_ms = ms;
-        cudaEventDestroy(t0);
-        cudaEventDestroy(t1);
-      }
-    };
-    // once-only parts: waves of independent ops (small ops of a wave = one launch; the other launches of a wave are
-    // spread over the caller's stream and a few side streams, joined before the next wave)
-    auto run_schedule = [&](std::vector<Launch>& sched) {
-      size_t li = 0;
-      while (li < sched.size()) {
-        size_t lj = li;
-        if (!timing && n_side_max > 0 && forkable(sched[li]))
-          while (lj < sched.size() && sched[lj].wave == sched[li].wave && forkable(sched[lj])) lj++;
-        const int group = (int)(lj - li);
-        if (group < 3) {
-          run_one(sched[li], stream);
-          li++;
-          continue;
-        }
-        const int n_side = std::min(n_side_max, group - 1);
-        while ((int)P.side.size() < n_side) {
-          cudaStream_t st;
-          TSB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-          P.side.push_back(st);
-        }
-        while ((int)P.side_ev.size() < 1 + n_side) {
-          cudaEvent_t e;
-          TSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-          P.side_ev.push_back(e);
-        }
-        TSB_CUDA(cudaEventRecord(P.side_ev[0], stream));
-        for (int q = 0; q < n_side; q++) TSB_CUDA(cudaStreamWaitEvent(P.side[q], P.side_ev[0], 0));
-        for (int g = 0; g < group; g++) {
-          const int lane = g % (n_side + 1);
-          run_one(sched[li + g], lane == 0 ? stream : P.side[lane - 1]);
-        }
-        for (int q = 0; q < n_side; q++) {
-          TSB_CUDA(cudaEventRecord(P.side_ev[1 + q], P.side[q]));
-          TSB_CUDA(cudaStreamWaitEvent(stream, P.side_ev[1 + q], 0));
-        }
-        li = lj;
-      }
-    };
-    // A rank that executes an aligned power-of-two block of slice ids computes only its own sub-blocks of the
-    // once-only tensors that keep sliced wires (run_step / pre_block); everything else is replicated.
-    P.rr_nfixed = 0;
-    P.rr_launches = 0;
-    {
-      static const bool restrict_pre = [] { const char* e = getenv("TSB_PRE_RESTRICT"); return !(e && e[0] == '0'); }();
-      const int64_t n = slice_end - slice_begin, total = P.info.n_slices;
-      bool binary = !P.sliced.empty();
-      for (auto w : P.sliced) binary = binary && P.wext[w] == 2;
-      if (restrict_pre && binary && n > 0 && n < total && (n & (n - 1)) == 0 && slice_begin % n == 0) {
-        P.rr_nfixed = (int)P.sliced.size() - ilog2(n);
-        P.rr_digits = slice_digits(P, slice_begin);
-      }
-    }
-    run_schedule(P.schedule);
-    P.rr_nfixed = 0;
-    // per-slice part
-    if (!P.sliced.empty()) {
-      for (int64_t sid = slice_begin; sid < slice_end; sid++) {
-        const std::vector<int64_t> digits = slice_digits(P, sid);
-        if (P.n_leaves == 1) {
-          // single tensor network with sliced wires: index the leaf, accumulate into the stacked buffer
-          const auto& lw = P.leaf_wires[0];
-          std::vector<int32_t> ext(lw.size()), fixed(lw.size(), -1), ports;
-          for (size_t q = 0; q < lw.size(); q++) {
-            ext[q] = P.wext[lw[q]];
-            for (size_t z = 0; z < P.sliced.size(); z++)
-              if (P.sliced[z] == lw[q]) fixed[q] = (int32_t)digits[z];
-          }
-          const PNode& r = P.nodes[P.rnode];
-          for (auto w : r.reg)
-            for (size_t q = 0; q < lw.size(); q++) if (lw[q] == w) { ports.push_back((int32_t)q); break; }
-          void* po = base + r.offset + shared_offset(P, r, digits) * dtype_size(r.dtype);
-          rewire_impl(ctx, leaf_ptrs[0], (int)lw.size(), ext.data(), fixed.data(), TSB_U8, po, (int)ports.size(),
-                      ports.data(), r.dtype, P.mode == TSB_SAT, true, stream);
-          continue;
-        }
-        for (int i : P.slice_ops) {
-          POp& op = P.ops[i];
-          timed((size_t)i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, stream); });
-        }
-      }
-    }
-    run_schedule(P.post_schedule);
-    if (P.mask_root) {
-      // out[o] = sum over sliced-wire combinations s in [slice_begin, slice_end) of root[s, o]
-      const PNode& r = P.nodes[P.root];
-      std::vector<uint8_t> mask((size_t)r.s_numel, 0);
-      for (int64_t sid = slice_begin; sid < slice_end; sid++) {
-        const std::vector<int64_t> digits = slice_digits(P, sid);
-        mask[(size_t)(shared_offset(P, r, digits) / r.reg_numel)] = 1;
-      }
-      uint8_t* d_mask = base + P.mask_offset;
-      TSB_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, stream));
-      const std::vector<int32_t> rw = r.stored();
-      contract2_impl(ctx, base + r.offset, (int)rw.size(), rw.data(), r.dtype, d_mask, (int)r.slab.size(), r.slab.data(),
-                     TSB_U8, out, (int)r.reg.size(), r.reg.data(), P.info.out_dtype, P.n_wires, P.wext.data(), P.mode, false,
-                     false, stream);
-    }
-    if (P.stack_out) {
-      // [sliced output wires][other output wires] -> requested output order
-      const PNode& r = P.nodes[P.rnode];
-      std::vector<int32_t> axes = r.stored(), ext(axes.size()), ports;
-      for (size_t q = 0; q < axes.size(); q++) ext[q] = P.wext[axes[q]];
-      for (auto w : P.out_wires)
-        for (size_t q = 0; q < axes.size(); q++) if (axes[q] == w) { ports.push_back((int32_t)q); break; }
-      rewire_impl(ctx, base + r.offset, (int)axes.size(), ext.data(), nullptr, r.dtype, out, (int)ports.size(),
-                  ports.data(), r.dtype, false, false, stream);
-    }
+    Temp block(ctx, (size_t)std::max<int64_t>(P.info.peak_bytes, 256), stream);
+    upload_ptrs(P, (uint8_t*)block.p, out, leaf_ptrs, stream);
+    enqueue_execution(P, (uint8_t*)block.p, leaf_ptrs, slice_begin, slice_end, out, mask, stream, P.timing, n_side_max);
+    mark_done();
     return TSB_OK;
   } catch (const tsb::Error& e) {
     return e.code;
@@ -1469,11 +1682,22 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
 
 int tsb_plan_destroy(tsb_plan* plan) {
   if (plan) {
+#ifndef TSB_HOST_EMU
+    if (plan->has_last && !plan->graphs.empty()) cudaStreamSynchronize(plan->last_stream);
+    for (auto& kv : plan->graphs) destroy_graph_entry(*plan, kv.second);
+#endif
+    try {
+      if (plan->gblock) plan->ctx->arena.release(plan->gblock, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
+      if (plan->gres) plan->ctx->arena.release(plan->gres, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
+    } catch (...) {
+    }
+    if (plan->done_ev) cudaEventDestroy(plan->done_ev);
     for (auto e : plan->ev) cudaEventDestroy(e);
     for (auto e : plan->side_ev) cudaEventDestroy(e);
     for (auto st : plan->side) cudaStreamDestroy(st);
     if (plan->d_small_ops) cudaFree(plan->d_small_ops);
     if (plan->d_ptrs) cudaFree(plan->d_ptrs);
+    tsb::ctx_unref(plan->ctx);
     delete plan;
   }
   return TSB_OK;

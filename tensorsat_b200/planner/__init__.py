@@ -1,7 +1,7 @@
 """Host-side planning: flat networks, contraction trees, slicing (not on the timed path)."""
 
 from .network import Network
-from .sampling import fix_wires, sample_subcube
+from .sampling import fix_wires, propagate_wire_values, sample_subcube
 from .search import find_tree
 from .tree import ContractionTree, TreeStats, linear_to_ssa, ssa_to_linear
 
@@ -12,6 +12,7 @@ __all__ = [
     "find_tree",
     "fix_wires",
     "sample_subcube",
+    "propagate_wire_values",
     "linear_to_ssa",
     "ssa_to_linear",
 ]

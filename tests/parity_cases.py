@@ -744,18 +744,73 @@ def test_arena_is_reused_across_executions():
 
     cnf = CNFInstance.random(3, 12, 50, rng=4)
     d = (cnf.inputs(None) >> cnf.diagram()).flatten()
+    base = _native.arena_stats()
     c = TreeContraction(CudaFinRel, d.wiring, trials=2)
     c.contract(d)
+    c.contract(d)   # (on the GPU the second execution is captured into a CUDA graph that owns its arena block)
     before = _native.arena_stats()
     for _ in range(3):
         c.contract(d)
     after = _native.arena_stats()
     assert after["device_allocs"] == before["device_allocs"]
-    assert after["cache_hits"] >= before["cache_hits"] + 3
+    replays = c.plan().describe()["graph_replays"]
+    assert replays >= 3 or after["cache_hits"] >= before["cache_hits"] + 3
     assert after["in_use_bytes"] == before["in_use_bytes"]
+    c.plan().close()   # a plan returns what its graphs held
+    assert _native.arena_stats()["in_use_bytes"] == base["in_use_bytes"]
 
 
 # ------------------------------------------------------------------------------------ autoray backend
+def test_arena_orders_reuse_across_streams():
+    """A block released on one stream and handed to another is ordered by an event (stream-aware arena); the
+    stream-less forms keep working; the bookkeeping survives threads."""
+    import ctypes as C
+    import threading
+
+    from tensorsat_b200 import _native
+
+    lib, ctx = _native.lib(), _native.ctx()
+    if _native._device == "cuda":
+        import torch
+
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        a, b = C.c_void_p(s1.cuda_stream), C.c_void_p(s2.cuda_stream)
+    else:
+        a, b = C.c_void_p(16), C.c_void_p(32)
+    n = 3 << 20
+    p, q = C.c_void_p(), C.c_void_p()
+    _native._check(lib.tsb_arena_alloc_async(ctx, C.c_size_t(n), a, C.byref(p)))
+    w0 = _native.arena_stats()["cross_stream_waits"]
+    _native._check(lib.tsb_arena_release_async(ctx, p, a))
+    _native._check(lib.tsb_arena_alloc_async(ctx, C.c_size_t(n), a, C.byref(q)))     # same stream: no wait needed
+    assert q.value == p.value and _native.arena_stats()["cross_stream_waits"] == w0
+    _native._check(lib.tsb_arena_release_async(ctx, q, a))
+    _native._check(lib.tsb_arena_alloc_async(ctx, C.c_size_t(n), b, C.byref(q)))     # other stream: ordered by the event
+    assert q.value == p.value and _native.arena_stats()["cross_stream_waits"] == w0 + 1
+    _native._check(lib.tsb_arena_release_async(ctx, q, b))
+    _native._check(lib.tsb_arena_alloc(ctx, C.c_size_t(n), C.byref(q)))              # stream-less: host-side wait
+    assert q.value == p.value and _native.arena_stats()["cross_stream_waits"] == w0 + 2
+    _native._check(lib.tsb_arena_release(ctx, q))
+    with pytest.raises(ValueError):
+        _native._check(lib.tsb_arena_release(ctx, q))    # double release is refused, not corrupted
+    errors = []
+
+    def worker():
+        try:
+            for _ in range(200):
+                r = C.c_void_p()
+                _native._check(lib.tsb_arena_alloc_async(ctx, C.c_size_t(1 << 12), a, C.byref(r)))
+                _native._check(lib.tsb_arena_release_async(ctx, r, a))
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker) for _ in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    st = _native.arena_stats()
+    assert not errors and st["in_use_bytes"] <= st["reserved_bytes"]
+
+
 def test_autoray_backend_functions():
     """einsum / tensordot / transpose / reshape / stack / shape with the reference's signatures (_autoray.py:31-80)."""
     from tensorsat_b200 import autoray_backend as ab
@@ -931,6 +986,48 @@ def test_weighted_counting_leaves_are_rejected_by_plans_and_exact_step_by_step()
     assert np.array_equal(res.tensor, np.ones((2, 2), np.int64))
     assert _native.all_binary(_native.upload(np.array([0, 1, 1, 0], np.uint8)))
     assert not _native.all_binary(_native.upload(np.array([0, 1, -1, 0], np.int64)))
+
+
+def test_witness_pinned_subcubes_are_exact():
+    """Sampled sub-cubes (planner.sampling / planner.subcube): pins that follow a known model give a sub-cube whose
+    answer is SAT with the exact sub-cube count; single flips and random pins agree with brute force and with the
+    independent exact counter (oracle/sharp_sat.py) — the small-scale twin of tests/test_gpu_wide_configs.py."""
+    from oracle.sharp_sat import count_models, network_to_cnf
+    from tensorsat_b200 import _native
+    from tensorsat_b200.planner import propagate_wire_values, sample_subcube
+
+    n = 16
+    cnf = CNFInstance.random(3, n, 64, rng=9)
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    model = [int(x) for x in np.argwhere(brute)[0]]
+    flat, net = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
+    leaves = [b.tensor for b in flat.boxes]
+    vals = propagate_wire_values(net, leaves, dict(enumerate(model)))
+    assert len(vals) == net.num_wires
+    tree = find_tree_elimination(net, trials=2, seed=0).slice_to(6)
+    assert len(tree.sliced_wires) >= 4
+    wcnf = network_to_cnf(net.inputs, leaves)
+    free = [w < n for w in range(net.num_wires)]
+    for witness, seed in ((vals, 0), (None, 1), (None, 2)):
+        sub, subleaves, asg = sample_subcube(tree, leaves, 2, seed=seed, witness=witness)
+        cases = [asg] + [{**asg, w: asg[w] ^ 1} for w in list(asg)[:3]]
+        for a in cases:
+            from tensorsat_b200.planner.sampling import fix_wires
+
+            net_a, leaves_a = fix_wires(net, leaves, a)
+            want = count_models(net.num_wires, wcnf, a)
+            if all(w < n for w in a):
+                idx = tuple(a.get(v, slice(None)) for v in range(n))
+                assert want == int(brute[idx].sum()) == count_models(n, cnf.clauses, a)
+            for mode in (_native.MODE_SAT, _native.MODE_COUNT):
+                plan = _native.Plan(net_a.inputs, net_a.output, net_a.size_dict, tree.ssa_path, sub.sliced_wires, mode=mode,
+                                    wire_is_free=free)
+                out = _native.empty(1, mode)
+                plan.execute([_native.upload(np.ascontiguousarray(t)) for t in leaves_a], out)
+                got = int(out.cpu().numpy()[0])
+                assert got == (want if mode == _native.MODE_COUNT else int(want > 0)), (a, mode, got, want)
+        if witness is not None:
+            assert count_models(net.num_wires, wcnf, asg) >= 1
 
 
 def test_slice_blocks_restrict_the_once_only_tensors():

@@ -92,3 +92,104 @@ def test_full_size_c1_properties():
         for clause in cnf.clauses:
             assert any((model[abs(l) - 1] == 1) == (l > 0) for l in clause)
         assert int(run(cnt_c, prefix)) == 1
+
+
+def test_plan_executions_replay_as_cuda_graphs(monkeypatch):
+    """From the second execution with the same slice range on, a plan replays its launch sequence as a CUDA graph
+    (one host call): results stay exact when only the leaf VALUES change between replays, the per-kernel counters
+    keep counting, TSB_PLAN_NO_GRAPH switches it off, and two slice ranges get two graphs."""
+    from oracle import fin_rel_oracle as O
+    from tensorsat_b200 import _native
+    from tensorsat_b200.contractions.tree import TreeContraction
+    from tensorsat_b200.lang.fin_rel import CudaCountRel, CudaFinRel
+    from tensorsat_b200.lib.sat import CNFInstance
+    from tensorsat_b200.planner import Network
+    from tensorsat_b200.planner.search import find_tree_elimination
+
+    monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")
+    n = 18
+    cnf = CNFInstance.random(3, n, 72, rng=3)
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    wiring = cnf.contraction_wiring()
+    tree = find_tree_elimination(Network.from_wiring(wiring), trials=2, seed=0)
+    tree = tree.slice_to(max(tree.width() - 3, 6))
+    assert tree.num_slices >= 4
+    free = [w < n for w in wiring.wires]
+    for cls, kw in ((CudaFinRel, {}), (CudaCountRel, {"wire_is_free": free})):
+        c = TreeContraction(cls, wiring, tree=tree, batch_log2=10, **kw)
+        specs = ["?" * n, "1" + "?" * (n - 1), "01" + "?" * (n - 2), "0" + "?" * (n - 1), "?" * n, "110" + "?" * (n - 3)]
+        for spec in specs:
+            flat = (cnf.inputs(spec) >> cnf.diagram()).flatten()
+            sub = brute[tuple(int(ch) for ch in spec if ch != "?")]
+            got = c.contract_from_host([b.tensor for b in flat.boxes])
+            assert (int(got) == int(sub.sum())) if cls is CudaCountRel else (bool(got) == bool(sub.any())), spec
+        d = c.plan().describe()
+        assert d["graph_captures"] == 1 and d["graph_replays"] == len(specs) - 1
+        # a second slice range: its own graph; halves combine to the whole
+        flat = (cnf.inputs(None) >> cnf.diagram()).flatten()
+        leaves = [b.tensor for b in flat.boxes]
+        h = c.num_slices // 2
+        for _ in range(3):
+            lo = c.contract_from_host(leaves, (0, h))
+            hi = c.contract_from_host(leaves, (h, c.num_slices))
+            whole = (int(lo) + int(hi)) if cls is CudaCountRel else int(bool(lo) or bool(hi))
+            assert whole == (int(brute.sum()) if cls is CudaCountRel else int(brute.any()))
+        assert c.plan().describe()["graph_captures"] == 3
+    # per-kernel counters count replayed launches too
+    c = TreeContraction(CudaFinRel, wiring, tree=tree, batch_log2=10)
+    flat = (cnf.inputs(None) >> cnf.diagram()).flatten()
+    leaves = [b.tensor for b in flat.boxes]
+    c.contract_from_host(leaves)
+    _native.trace(True)
+    before = _native.launch_count()
+    c.contract_from_host(leaves)
+    direct = (_native.launch_count() - before, {k: v for k, v in _native.kernel_counts().items() if v})   # capture + first replay
+    _native.trace(True)
+    before = _native.launch_count()
+    c.contract_from_host(leaves)
+    replay = (_native.launch_count() - before, {k: v for k, v in _native.kernel_counts().items() if v})
+    _native.trace(False)
+    assert c.plan().describe()["graph_replays"] == 2
+    assert replay[0] == direct[0] > 0 and replay[1] == direct[1]
+    assert any(k.startswith("k_merge_bits") for k in replay[1])
+    # switched off per plan
+    import tensorsat_b200.contractions.tree as T
+
+    c2 = TreeContraction(CudaFinRel, wiring, tree=tree, batch_log2=10)
+    c2._flags |= _native.PLAN_NO_GRAPH
+    for _ in range(3):
+        assert bool(c2.contract_from_host(leaves)) == bool(brute.any())
+    d2 = c2.plan().describe()
+    assert d2["graph_captures"] == 0 and d2["graph_replays"] == 0
+    assert T is not None
+
+
+def test_plans_are_safe_across_streams():
+    """Executions of one plan issued on different streams are serialised by the plan (event wait), and the arena
+    hands blocks across streams in order: alternating streams gives the same answers."""
+    import torch
+
+    from oracle import fin_rel_oracle as O
+    from tensorsat_b200.contractions.tree import TreeContraction
+    from tensorsat_b200.lang.fin_rel import CudaCountRel
+    from tensorsat_b200.lib.sat import CNFInstance
+    from tensorsat_b200.planner import Network
+    from tensorsat_b200.planner.search import find_tree_elimination
+
+    n = 16
+    cnf = CNFInstance.random(3, n, 60, rng=4)
+    brute = O.cnf_brute_force(n, cnf.clauses).reshape((2,) * n)
+    wiring = cnf.contraction_wiring()
+    tree = find_tree_elimination(Network.from_wiring(wiring), trials=2, seed=0).slice_to(9)
+    c = TreeContraction(CudaCountRel, wiring, tree=tree, wire_is_free=[w < n for w in wiring.wires])
+    streams = [torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()]
+    outs = []
+    for i in range(9):
+        spec = format(i % 4, "02b") + "?" * (n - 2)
+        flat = (cnf.inputs(spec) >> cnf.diagram()).flatten()
+        with torch.cuda.stream(streams[i % 3]):
+            outs.append((spec, c.contract(flat)))
+    torch.cuda.synchronize()
+    for spec, box in outs:
+        assert int(box) == int(brute[int(spec[0]), int(spec[1])].sum()), spec

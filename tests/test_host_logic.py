@@ -175,3 +175,28 @@ def test_slice_blocks_partition_all_slices():
             assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
     with pytest.raises(ValueError):
         slice_block(4, 2, 2)
+
+
+def test_subcube_plan_files_are_consistent():
+    """bench_plans/subcube_*.json (tools/make_subcube_plans.py): the committed witnesses are solutions, the pins of a
+    sub-cube follow them, the sub-cubes are non-empty by the independent exact counter, and the trees fit the
+    2^30-entry budget the benchmarks quote."""
+    from oracle.sharp_sat import count_models
+    from tensorsat_b200.planner import subcube
+
+    for config, n, m in (("c2", 120, 511), ("c4", 200, 852)):
+        f = subcube.load(config)
+        cnf = CNFInstance.random(3, n, m, rng=0)
+        model = f.extra["model"]
+        assert all(any((model[abs(l) - 1] == 1) == (l > 0) for l in c) for c in cnf.clauses)
+        assert f.tree.network.num_leaves == len(f.leaves) and f.tree.width() <= 30
+        sub, subleaves, asg = f.subcube(4)
+        assert sub.num_slices == 16 and all(model[w] == v for w, v in asg.items())
+        assert count_models(n, cnf.clauses, asg) >= 1
+        assert len(asg) == len(f.tree.sliced_wires) - 4 and sub.width() <= 30
+    assert count_models(120, CNFInstance.random(3, 120, 511, rng=0).clauses) == 195572   # #SAT of BASELINE config 2
+    f = subcube.load("c5")
+    assert f.extra["factors"] == [65521, 65519] and f.tree.width() <= 30
+    sub, subleaves, asg = f.subcube(2)
+    for ws, t in zip(sub.network.inputs, subleaves):
+        assert t.ndim == len(ws)

@@ -8,10 +8,12 @@ Per-slice throughput of the BASELINE configurations that are too wide to contrac
     python tools/sampled_slices.py --config c5      # 16x16 Wallace multiplier, product fixed to 65521*65519
     torchrun --nproc-per-node 8 ... tools/sampled_slices.py --config c4   # slices split over ranks
 
-The tree (elimination order, 1 trial) is sliced to 2^30-entry intermediates (`slice_to_fast`), all but the
-last `--keep` sliced wires are pinned to seeded random values on the host, and the remaining 2^keep slices
-are executed exactly like any other plan.  The printed result is the exact answer for that sub-cube of the
-assignment space ONLY; the number of slices of the full instance is printed next to it.
+The tree (elimination order, 1 trial, sliced to 2^30-entry intermediates) comes from the committed plan files
+bench_plans/subcube_*.json (tools/make_subcube_plans.py); all but the last `--keep` sliced wires are pinned on the
+host ALONG A KNOWN SOLUTION of the instance (a committed model / the factors 65521 x 65519; `--random-pins` pins
+seeded random values instead), and the remaining 2^keep slices are executed exactly like any other plan.  The
+printed result is the exact answer for that sub-cube of the assignment space ONLY and is checked against the
+independent exact counter (oracle/sharp_sat.py) where that finishes in seconds.
 """
 import argparse
 import json
@@ -25,27 +27,6 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def build(config):
-    from tensorsat_b200.diagrams import DiagramBuilder
-    from tensorsat_b200.lib import bincirc as bc
-    from tensorsat_b200.lib.sat import CNFInstance
-
-    if config in ("c2", "c4"):
-        n, m = (120, 511) if config == "c2" else (200, 852)
-        cnf = CNFInstance.random(3, n, m, rng=0)
-        d = (cnf.inputs(None) >> cnf.diagram()).flatten()
-        return d, [w < n for w in d.wiring.wires], f"random 3-SAT n={n} m={m} seed=0", ("count" if config == "c2" else "sat")
-    nbits, N = 16, 65521 * 65519
-    mult = bc.wallace_multiplier(nbits)
-    b = DiagramBuilder()
-    ins = [(bc.bit_unk @ b)[0] for _ in range(2 * nbits)]
-    outs = mult @ b[ins]
-    for i, w in enumerate(outs):
-        (bc.bit_1 if (N >> i) & 1 else bc.bit_0) @ b[w]
-    d = b.diagram().flatten()
-    return d, [w < 2 * nbits for w in d.wiring.wires], f"wallace_multiplier(16) with the product fixed to 65521*65519", "sat"
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4", choices=["c2", "c4", "c5"])
@@ -54,14 +35,14 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="time every launch of one slice and print the slowest ops")
+    ap.add_argument("--random-pins", action="store_true", help="pin seeded random values (round-1 behaviour: an empty sub-cube)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
 
     from tensorsat_b200 import _native
     from tensorsat_b200.distributed import all_reduce_result, slice_block
-    from tensorsat_b200.planner import Network, sample_subcube
-    from tensorsat_b200.planner.search import find_tree_elimination
+    from tensorsat_b200.planner import subcube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -69,12 +50,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     t0 = time.time()
-    diagram, free, name, mode_name = build(args.config)
-    net = Network.from_diagram(diagram)
-    tree = find_tree_elimination(net, trials=1, seed=0)
-    full = tree.slice_to_fast(args.target)
-    leaves = [b.tensor for b in diagram.boxes]
-    sub, subleaves, assignment = sample_subcube(full, leaves, args.keep, seed=args.seed)
+    f = subcube.load(args.config)
+    full, net, free, name, mode_name = f.tree, f.tree.network, f.wire_is_free, f.description, f.mode
+    sub, subleaves, assignment = f.subcube(args.keep, witness=not args.random_pins, seed=args.seed)
     plan_time = time.time() - t0
     mode = _native.MODE_COUNT if mode_name == "count" else _native.MODE_SAT
     plan = _native.Plan(sub.network.inputs, sub.network.output, sub.network.size_dict, sub.ssa_path, sub.sliced_wires,
@@ -154,18 +132,28 @@ def main():
         except Exception:
             pass
         alg = plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n
-        st_full, st_tree = full.stats(), tree.stats()
+        expected = None
+        if args.config in ("c2", "c4"):
+            from oracle.sharp_sat import count_models
+            from tensorsat_b200.lib.sat import CNFInstance
+
+            cnf = CNFInstance.random(3, f.n_vars, 511 if args.config == "c2" else 852, rng=0)
+            expected = count_models(f.n_vars, cnf.clauses, assignment)
+            expected = expected if mode_name == "count" else int(expected > 0)
+        elif not args.random_pins:
+            expected = 1
         print(json.dumps({
             "config": args.config, "instance": name, "mode": mode_name, "n_gpus": world,
-            "leaves": net.num_leaves, "wires": net.num_wires, "tree_log2_width": st_tree.log2_max_size,
+            "leaves": net.num_leaves, "wires": net.num_wires, "tree_log2_width": f.extra["tree_log2_width"],
             "sliced_wires_total": len(full.sliced_wires), "log2_slices_full_instance": len(full.sliced_wires),
-            "slices_executed": int(n), "sampled": f"{len(assignment)} sliced wires pinned to seeded random values (seed {args.seed})",
+            "slices_executed": int(n), "sampled": f"{len(assignment)} sliced wires pinned " + (f"to seeded random values (seed {args.seed})" if args.random_pins else "along a committed solution of the instance"),
             "ms_total": ms, "ms_per_slice": ms / n * 1.0, "alg_bytes_executed": alg, "GBps": alg / (ms * 1e-3) / 1e9,
             "frac_hbm_per_gpu": alg / (ms * 1e-3) / 1e9 / peak / world, "peak_arena_bytes": int(plan.info["peak_bytes"]),
             "kernels_once": plan.info["n_kernels_shared"], "kernels_per_slice": plan.info["n_kernels_per_slice"],
-            "subcube_result": int(out.cpu().numpy().reshape(-1)[0]), "host_planning_s": round(plan_time, 1),
+            "subcube_result": int(out.cpu().numpy().reshape(-1)[0]), "subcube_expected_by_exact_counter": expected, "host_load_s": round(plan_time, 1),
             "extrapolated_full_instance_s": (ms / n) * 1e-3 * 2.0 ** len(full.sliced_wires),
         }))
+        assert expected is None or int(out.cpu().numpy().reshape(-1)[0]) == expected
     if world > 1:
         dist.destroy_process_group()
 
