@@ -143,10 +143,10 @@ def hbm_peak() -> tuple[float, str]:
 _FINE: dict = {}
 
 
-def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22) -> dict:
+def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22, offset: int = 0) -> dict:
     """The reference arithmetic (numpy oracle) on a bounded sample of the same plan: the tree is sliced
-    further so that one slice fits the host comfortably, `n_sample` slices are timed and the whole-job
-    time is extrapolated (slices have identical shapes and cost)."""
+    further so that one slice fits the host comfortably, `n_sample` slices (evenly spread, shifted by `offset`)
+    are timed and the whole-job time is extrapolated (slices have identical shapes and cost)."""
     from oracle import fin_rel_oracle as O
 
     key = (id(tree), target_log2)
@@ -155,102 +155,55 @@ def cpu_sample(tree, diagram, n_sample: int, target_log2: int = 22) -> dict:
     fine = _FINE[key]
     leaves = [b.tensor for b in diagram.boxes]
     n = fine.num_slices
-    ids = [int(i * n / n_sample) for i in range(n_sample)]
+    ids = sorted({(int(i * n / n_sample) + offset) % n for i in range(n_sample)})
     net = fine.network
-    O.execute_tree(net.inputs, net.output, leaves, fine.ssa_path, fine.sliced_wires, slice_ids=ids[:1], size_dict=net.size_dict)
+    if "warm" not in _FINE:
+        O.execute_tree(net.inputs, net.output, leaves, fine.ssa_path, fine.sliced_wires, slice_ids=ids[:1], size_dict=net.size_dict)
+        _FINE["warm"] = True
     t0 = time.perf_counter()
     O.execute_tree(net.inputs, net.output, leaves, fine.ssa_path, fine.sliced_wires, slice_ids=ids, size_dict=net.size_dict)
     dt = time.perf_counter() - t0
-    est = dt / n_sample * n
+    est = dt / len(ids) * n
     return {"value": est, "unit": "s", "cores": 1, "kind": "port",
-            "host_cores_available": os.cpu_count(),
-            "sample": (f"numpy oracle (reference arithmetic, single-threaded integer einsum) on {n_sample} of {n} slices "
+            "host_cores_available": os.cpu_count(), "measured_s": dt, "slices_measured": len(ids), "slices_total": n,
+            "sample": (f"numpy oracle (reference arithmetic, single-threaded integer einsum) on {len(ids)} of {n} slices "
                        f"of the same tree sliced to 2^{target_log2}-entry intermediates, {dt:.2f} s measured, "
-                       f"extrapolated x{n / n_sample:.0f}")}
-
-
-def c4_subcube_leg(world: int, rank: int, keep: int, steps: int) -> dict | None:
-    """BASELINE config 4 (random 3-SAT n=200 m=852 seed 0, the north-star's sliced multi-GPU instance) on a SAMPLED
-    sub-cube: the tree (width 136) is sliced to 2^30-entry intermediates = 2^106 slices; all but `keep` sliced
-    wires are pinned along a committed model of the instance, the remaining 2^keep slices are split over the
-    ranks in contiguous blocks and combined by one all-reduce (max).  The sub-cube contains the model, so its
-    exact answer is SAT (checked)."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    from tensorsat_b200 import _native
-    from tensorsat_b200.distributed import all_reduce_result, slice_block
-    from tensorsat_b200.planner import subcube
-
-    if not os.path.exists(subcube.path_of("c4")):
-        return None
-    f = subcube.load("c4")
-    sub, subleaves, asg = f.subcube(keep)
-    net = sub.network
-    plan = _native.Plan(net.inputs, net.output, net.size_dict, sub.ssa_path, sub.sliced_wires, mode=_native.MODE_SAT)
-    leaves = [_native.upload(np.ascontiguousarray(t, dtype=np.uint8)) for t in subleaves]
-    out = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
-    n = int(plan.info["n_slices"])
-    lo, hi = slice_block(n, rank, world)
-
-    def step() -> None:
-        plan.execute(leaves, out, lo, hi)
-        if world > 1:
-            all_reduce_result(out, _native.MODE_SAT)
-
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in evs:
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
-    result = int(out.cpu().numpy().reshape(-1)[0])
-    info = plan.info
-    alg = info["alg_bytes_shared"] + info["alg_bytes_per_slice"] * n
-    res = {
-        "workload": (f"{f.description}; elimination-order tree (width {f.extra['tree_log2_width']:.0f}) sliced to 2^30-entry "
-                     f"intermediates = 2^{f.extra['n_sliced']} slices of the full instance; SAMPLED: {len(asg)} sliced wires pinned "
-                     f"along a committed model, the other 2^{keep} = {n} slices executed"),
-        "value": ms * 1e-3, "unit": "s", "ms_per_slice": ms / max(hi - lo, 1), "n_slices": n, "slices_per_rank": int(hi - lo),
-        "steps": steps, "scaling": "strong", "result": "SAT" if result else "UNSAT", "expected": "SAT (the sub-cube contains the model)",
-        "kernels_once": int(info["n_kernels_shared"]), "kernels_per_slice": int(info["n_kernels_per_slice"]),
-        "alg_bytes_moved_per_contraction": alg, "alg_GBps": alg / (ms * 1e-3) / 1e9,
-        "peak_arena_bytes": int(info["peak_bytes"]), "timing": "CUDA events per contraction incl. the all-reduce, max over ranks",
-    }
-    assert result == 1, "the sampled sub-cube of config 4 contains a model: the contraction must say SAT"
-    plan.close()
-    return res
+                       f"extrapolated x{n / len(ids):.0f}")}
 
 
 def run_reference(args) -> None:
+    """The reference's CPU arithmetic on this box's host cores.  A whole contraction takes about ten minutes of numpy
+    (one core: numpy's integer einsum is single-threaded and the reference runs slices one after another), so every
+    step times a BOUNDED sample of the slices — a different, evenly spread subset per step, sized so that the
+    whole run spends about two minutes measuring — and extrapolates by the slice count (all slices have the same
+    shapes and cost).  `measured_s_total` and the number of distinct slices measured are printed with the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cnf, diagram, tree = load_tree()
+    n_steps = args.warmup + args.steps
+    probe = cpu_sample(tree, diagram, n_sample=4)
+    per_slice = probe["measured_s"] / probe["slices_measured"]
+    budget_s = float(os.environ.get("TSB_REF_BUDGET_S", "120"))
+    n_per_step = int(max(4, min(probe["slices_total"] // max(n_steps, 1), budget_s / max(n_steps, 1) / per_slice)))
     vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_sample(tree, diagram, n_sample=4)
+    for i in range(n_steps):
+        r = cpu_sample(tree, diagram, n_sample=n_per_step, offset=1 + i * 7)
         if i >= args.warmup:
             vals.append(r)
     v = sum(x["value"] for x in vals) / len(vals)
+    measured = sum(x["measured_s"] for x in vals)
+    n_meas = sum(x["slices_measured"] for x in vals)
     line = {
         "impl": "reference", "metric": "random 3-SAT contraction time", "value": v, "unit": "s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_slices": tree.num_slices},
-        "cpu_baseline": {**vals[-1], "value": v},
+        "cpu_baseline": {**vals[-1], "value": v, "measured_s_total": measured, "slices_measured_total": n_meas,
+                         "sample": (f"numpy oracle (reference arithmetic, single-threaded integer einsum): {args.steps} timed steps x {n_per_step} slices "
+                                    f"= {n_meas} of {vals[-1]['slices_total']} slices of the same tree sliced to 2^22-entry intermediates "
+                                    f"(a different evenly spread subset per step), {measured:.1f} s measured in total, each step extrapolated "
+                                    f"x{vals[-1]['slices_total'] / n_per_step:.0f}")},
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -266,6 +219,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pack", action="store_true", help="keep boolean intermediates at one byte per entry (A/B runs)")
     ap.add_argument("--batch-log2", type=int, default=None, help="override the plan's once-only size limit (experiments)")
+    ap.add_argument("--no-micro", action="store_true", help="skip the permute / GEMM roofline micro-benchmarks")
     ap.add_argument("--c4-keep", type=int, default=10, help="config-4 sub-cube leg: 2^keep slices (0 < keep; -1: skip the leg)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -373,26 +327,36 @@ def main() -> None:
     # ---- the north-star's sliced instance (config 4) on a sampled sub-cube, same ranks
     c4 = c4_subcube_leg(world, rank, args.c4_keep, steps=3) if args.c4_keep > 0 else None
 
-    # ---- per-kernel roofline: instrumented pass (CUDA events around every launch of the plan)
+    # ---- roofline of the dominant kernel.  Time base: CUDA events at the PHASE boundaries of an execution
+    # (tsb_plan_set_timing(plan, 2): start | once-only schedule done | slice loop done | end), no event and no host
+    # synchronisation inside a phase, so the launches of the slice loop keep their programmatic overlap exactly as in
+    # the timed region; the slice loop of this plan consists of the k_merge_bits_f launches only.
     roof = None
+    roof_extra = {}
     if rank == 0:
-        plan.set_timing(True)
-        plan.execute(leaves_dev, out, lo, hi)
-        torch.cuda.synchronize()
+        plan.set_timing(2)
+        n_ph = min(args.steps, 20)
+        acc = {"pre": 0.0, "slice_loop": 0.0, "post": 0.0}
+        for _ in range(n_ph):
+            flush.fill_(1)
+            plan.execute(leaves_dev, out, lo, hi)
+            torch.cuda.synchronize()
+            ph = plan.describe()["phase_ms"]
+            for k in acc:
+                acc[k] += ph[k] / n_ph
+        plan.set_timing(0)
         desc = plan.describe()
-        plan.set_timing(False)
         peak, peak_src = hbm_peak()
         share = (hi - lo) if n_slices > 1 else 1
-        # dominant kernel: the per-slice merge launches (the large middle of the tree); k_merge_bits when the plan
-        # runs them bit-packed (bytes = 1/8 per entry, the representation the kernel actually moves), else k_merge_sat
         packed = plan.info["n_packed_steps"] > 0
-        kind = "bits" if packed else "merge"
-        merge = [o for o in desc["ops"] if o["kind"] == kind and (o["per_slice"] or n_slices == 1)]
-        mbytes = sum(o["bytes"] * (share if o["per_slice"] else 1) for o in merge)
-        mms = sum(o["ms"] for o in merge)
-        all_ms = sum(o["ms"] for o in desc["ops"])
-        n_launch = sum((share if o["per_slice"] else 1) for o in merge)
-        achieved = mbytes / (mms * 1e-3) / 1e9 if mms > 0 else 0.0
+        loop_ops = [o for o in desc["ops"] if o["per_slice"]]
+        dominant = [o for o in loop_ops if o["kind"] == ("bits" if packed else "merge")]
+        only_dominant = len(dominant) == len(loop_ops) and n_slices > 1
+        mbytes = sum(o["bytes"] for o in dominant) * share
+        n_launch = len(dominant) * share
+        loop_ms = acc["slice_loop"]
+        step_ms_phase = acc["pre"] + acc["slice_loop"] + acc["post"]
+        achieved = mbytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "bits_traffic.json" if packed else "merge_traffic.json")
         if os.path.exists(tp):
@@ -401,15 +365,30 @@ def main() -> None:
                     traffic = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": ("k_merge_bits_f<NOPS,KB,MASKS,NP> (fused bit-packed steps)" if packed else "k_merge_sat<NIBL,NIBR>") + ", per-slice launches",
+        # what the kernel is actually bound by: 16-byte operand fetches + result stores through the L1 data path
+        # (ncu: l1tex__data_pipe_lsu_wavefronts, lts__t_sectors_srcunit_tex_op_read; DRAM traffic is far below the launch bytes)
+        l1_bytes = sum((o["fetches_x4"] / 4.0 + 1.0) * 16.0 * 2.0 ** (o["out_bits"] - 7) for o in dominant) * share
+        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        l1_peak = 148 * 128 * sm_hz * 1e6 / 1e9
+        roof = {"bound": "hbm", "kernel": ("k_merge_bits_f<NOPS,KB,MASKS,NP> (fused bit-packed steps)" if packed else "k_merge_sat<NIBL,NIBR>") + ", the launches of the slice loop",
                 "bytes_counted": ("operands + result of each launch at 1/8 byte per entry; intermediates of the fused steps are not stored and not counted"
                                   if packed else "operands + result of each step at 1 byte per entry"),
                 "bytes_per_entry": 0.125 if packed else 1, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "alg_bytes_per_launch": mbytes / max(n_launch, 1), "avg_launch_ms": mms / max(n_launch, 1),
-                "launches_per_step": n_launch, "share_of_step": mms / all_ms if all_ms else None,
+                "alg_bytes_per_launch": mbytes / max(n_launch, 1), "avg_launch_ms": loop_ms / max(n_launch, 1),
+                "launches_per_step": n_launch,
+                "time_base": (f"CUDA events at the boundaries of the slice loop ({n_launch} back-to-back launches, no event inside), "
+                              f"mean of {n_ph} L2-flushed executions; slice loop holds only these launches: {only_dominant}"),
+                "phase_ms": acc, "step_ms_in_this_pass": step_ms_phase, "share_of_step": loop_ms / step_ms_phase if step_ms_phase else None,
+                "sum_le_step": bool(loop_ms <= ms_per_step * 1.02),
+                "actual_bound": {"what": "16-byte operand fetches and result stores through L1 (operands are L2-resident broadcast twins)",
+                                 "l1_bytes_per_step": l1_bytes, "achieved_GBps": l1_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms else None,
+                                 "peak_GBps": l1_peak, "frac": (l1_bytes / (loop_ms * 1e-3) / 1e9 / l1_peak) if loop_ms else None,
+                                 "peak_is": "148 SMs x 128 B/clk x SM clock", "ncu_counters": "l1tex__data_pipe_lsu_wavefronts.sum, lts__t_sectors_srcunit_tex_op_read.sum, smsp__issue_active"},
                 "whole_step_alg_GBps": (plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * share)
                 / (ms_per_step * 1e-3) / 1e9}
+        if world == 1 and not args.no_micro:
+            roof_extra = micro_rooflines(peak, peak_src)
 
     if rank == 0:
         cpu = None
@@ -429,7 +408,8 @@ def main() -> None:
                        "bit_packed_steps": int(plan.info["n_packed_steps"]), "conversions": int(plan.info["n_conversions"]),
                        "cuda_graph": {k: desc_graph[k] for k in ("graph_captures", "graph_replays")},
                        "c4_subcube": c4},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_permute": roof_extra.get("permute"), "roofline_gemm": roof_extra.get("gemm"),
+            "cpu_baseline": cpu,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": contraction.h2d_bytes,
                     "d2h_bytes_per_step": contraction.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -247,7 +247,13 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
  * device tensor of leaf i in its own axis order. */
 int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice_begin,
                      int64_t slice_end, void* out, tsb_stream stream);
-/* Per-kernel device times (ms) of the last execution with timing enabled; see tsb_plan_set_timing. */
+/* Timing of executions (device time, CUDA events on the launching stream), reported by tsb_plan_describe:
+ *   1: an event pair and a host synchronisation around EVERY launch ("ms" per op; serialises the launches and
+ *      removes their overlap: per-op shares for tools, not for totals);
+ *   2: four events at the phase boundaries of an execution, no host synchronisation ("phase_ms": once-only
+ *      schedule / slice loop / tail + combine, valid once the stream has been synchronised): what bench.py's
+ *      roofline uses, the launches inside a phase keep their programmatic overlap;
+ *   0: off.  Timed executions launch directly (no CUDA-graph replay). */
 int tsb_plan_set_timing(tsb_plan* plan, int enabled);
 int tsb_plan_timing_json(tsb_plan* plan, char* buf, size_t cap, size_t* needed);
 int tsb_plan_destroy(tsb_plan* plan);

@@ -395,8 +395,9 @@ class Plan:
         _check(lib().tsb_plan_execute(self._h, arr, C.c_int64(int(slice_begin)), C.c_int64(int(slice_end)),
                                       C.c_void_p(int(out_ptr)), stream()))
 
-    def set_timing(self, enabled: bool) -> None:
-        _check(lib().tsb_plan_set_timing(self._h, int(bool(enabled))))
+    def set_timing(self, enabled: bool | int) -> None:
+        """0 / False: off; 1 / True: per-launch (host-synchronised); 2: phase boundaries only (include/tsb.h)."""
+        _check(lib().tsb_plan_set_timing(self._h, int(enabled)))
 
     def describe(self) -> dict[str, Any]:
         import json

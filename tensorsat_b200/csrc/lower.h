@@ -131,6 +131,12 @@ struct Arena {
   }
 };
 
+// temporaries of a captured execution: owned by the graph (replays use the same addresses), recycled within the capture
+struct HeldBlocks {
+  std::vector<void*> owned;
+  std::multimap<size_t, void*> free;
+};
+
 }  // namespace tsb
 
 struct tsb_ctx {
@@ -148,7 +154,7 @@ struct tsb_ctx {
     if (cap_counts) (*cap_counts)[kernel]++;
   }
   tsb::Arena arena;
-  std::vector<void*>* hold = nullptr;              // set while a plan execution is captured into a CUDA graph
+  tsb::HeldBlocks* hold = nullptr;                 // set while a plan execution is captured into a CUDA graph
   std::map<std::string, int64_t>* cap_counts = nullptr;  // per-kernel launches of the execution being captured
   int* d_flag = nullptr;  // scratch for all_ones
   uint8_t* d_one = nullptr;  // the u8 scalar 1
@@ -166,12 +172,28 @@ struct Temp {
   tsb_ctx* ctx;
   cudaStream_t stream;
   void* p = nullptr;
+  size_t size = 0;
   Temp(tsb_ctx* c, size_t bytes, cudaStream_t s) : ctx(c), stream(s) {
-    p = c->arena.alloc(bytes, c->hold ? tsb::Arena::no_stream() : s);
+    if (c->hold) {
+      // capture: the launches are recorded in stream order, so a temporary released earlier in the capture can serve a
+      // later one; the graph ends up owning each distinct block once
+      size = tsb::Arena::round_up(bytes);
+      auto it = c->hold->free.lower_bound(size);
+      if (it != c->hold->free.end() && it->first <= size * 2 + (size_t(1) << 20)) {
+        p = it->second;
+        size = it->first;
+        c->hold->free.erase(it);
+      } else {
+        p = c->arena.alloc(bytes, tsb::Arena::no_stream());
+        c->hold->owned.push_back(p);
+      }
+      return;
+    }
+    p = c->arena.alloc(bytes, s);
   }
   ~Temp() {
     if (!p) return;
-    if (ctx->hold) ctx->hold->push_back(p);
+    if (ctx->hold) ctx->hold->free.emplace(size, p);
     else ctx->arena.release(p, stream);
   }
   Temp(const Temp&) = delete;
@@ -617,7 +639,7 @@ struct BitsFArgs {
 };
 
 inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
-                                  int n_top_excluded = 0, bool choose_lanes = false) {
+                                  int n_top_excluded = 0, bool choose_lanes = false, bool choose_tile = false) {
   BitsFArgs m;
   const int R = (int)out_bits.size(), n = (int)operands.size();
   if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
@@ -755,6 +777,37 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
       m.wf_chosen = best_cost;
       for (int q = 0; q < 4; q++) lanes.push_back(cand[bi[q]]);
     }
+  }
+  // Which output wires index the vectors of one CTA tile.  The operands of these steps are small next to the result
+  // (each lacks many output wires): with the tile spanned by wires that FEW operand fetches depend on, the part of
+  // every operand a tile touches shrinks to a few KB and is re-read from L1 instead of L2.  Greedy: starting from
+  // output bit 7, add the wire whose holders have the smallest footprint so far (ties: the lower bit).
+  if (choose_tile && lanes.empty() && vr > d.tile_bits) {
+    std::vector<double> fp(n);
+    for (int o = 0; o < n; o++) {
+      fp[o] = (double)(1 << __builtin_popcount((unsigned)kmask[o]));
+      for (int q = 0; q < NP; q++) if (lp[o].count(out_bits[R - 1 - pair_pos[q]])) fp[o] *= 2;
+      if (lp[o].count(out_bits[R - 1 - 7])) fp[o] *= 2;
+    }
+    std::vector<int> cand;
+    for (int j = 8; j < R - n_top_excluded; j++)
+      if (std::find(pair_pos.begin(), pair_pos.end(), j) == pair_pos.end()) cand.push_back(j);
+    while ((int)lanes.size() < d.tile_bits - 1 && !cand.empty()) {
+      int best = -1;
+      double best_cost = 0;
+      for (int c = 0; c < (int)cand.size(); c++) {
+        double cost = 0;
+        for (int o = 0; o < n; o++) if (lp[o].count(out_bits[R - 1 - cand[c]])) cost += fp[o];
+        if (best < 0 || cost < best_cost) { best = c; best_cost = cost; }
+      }
+      const int j = cand[best];
+      cand.erase(cand.begin() + best);
+      lanes.push_back(j);
+      for (int o = 0; o < n; o++) if (lp[o].count(out_bits[R - 1 - j])) fp[o] *= 2;
+    }
+    double total = 0;
+    for (int o = 0; o < n; o++) total += fp[o];
+    m.wf_chosen = (long)total;   // 16-byte vectors of all operands one tile touches
   }
   std::vector<int> index_bits;  // reduced index bit -> output bit
   index_bits.push_back(7);

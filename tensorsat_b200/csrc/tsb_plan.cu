@@ -139,7 +139,10 @@ struct tsb_plan {
   bool stack_out = false;       // some output wire is sliced: per-slice results land in `rbuf`
   int rnode = -1;               // pseudo node for rbuf
   std::vector<int32_t> rbuf_axes;
-  bool timing = false;
+  int timing = 0;                      // 0: off; 1: an event pair + host sync around every launch (tools); 2: four
+                                       // events at the phase boundaries of an execution, no host sync (bench.py)
+  cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start | pre done | slice loop done | end
+  bool phase_valid = false;
   std::vector<cudaEvent_t> ev;
   std::vector<Launch> schedule;        // once-only part before the slice loop, in launch order
   std::vector<Launch> post_schedule;   // once-only part after the slice loop (re-batched tail of the tree)
@@ -167,7 +170,7 @@ struct tsb_plan {
   };
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
-    std::vector<void*> held;                   // temporaries of the captured launches (owned until the graph dies)
+    tsb::HeldBlocks held;                      // temporaries of the captured launches (owned until the graph dies)
     std::map<std::string, int64_t> kcount;     // kernels per replay
     int64_t launches = 0;
     int rr_launches = 0;
@@ -176,6 +179,8 @@ struct tsb_plan {
   std::map<GraphKey, GraphEntry> graphs;
   std::map<GraphKey, int> seen;          // executions per key so far (capture on the second)
   std::set<GraphKey> ungraphable;        // capture failed once: always direct
+  cudaStream_t cap_stream = nullptr;     // capture happens on a stream of the plan's own (the caller's may be the
+                                         // legacy default stream, which cannot be captured); replays go to the caller's
   void* gblock = nullptr;                // arena block owned by the graphs of this plan (same addresses on replay)
   void* gres = nullptr;                  // small results land here inside a graph, then one D2D copy to the caller
   uint64_t tick = 0;
@@ -776,7 +781,10 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
             int n_slab_bits = 0;
             if (P.nodes[y].shared)
               for (auto w : P.nodes[y].slab) n_slab_bits += ilog2(P.wext[w]);
-            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 0.0) != 0.0);
+            BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 0.0) != 0.0,
+                                           env_or("TSB_FUSE_TILE", 0.0) != 0.0);
+            if (!f.ok && env_or("TSB_FUSE_TILE", 0.0) != 0.0)   // too many bit runs for the tables: plain order
+              f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, false, false);
             if (f.ok) { op.fd = f.d; op.use_f = true; op.wf_chosen = f.wf_chosen; op.wf_default = f.wf_default; }
           }
           P.info.n_fused_steps += op.n_fused;
@@ -1232,7 +1240,16 @@ static int fetches_x4(const POp& op) {
 int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* needed) {
   if (!plan || !needed) { tsb::set_error("null argument"); return TSB_ERR_INVALID; }
   std::ostringstream os;
-  os << "{\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices
+  os << "{";
+  if (plan->phase_valid && plan->phase_ev[3] && cudaEventQuery(plan->phase_ev[3]) == cudaSuccess) {
+    // device times of the last execution with phase timing: [once-only schedule | slice loop | tail + combine]
+    float pre = 0, loop = 0, post = 0;
+    cudaEventElapsedTime(&pre, plan->phase_ev[0], plan->phase_ev[1]);
+    cudaEventElapsedTime(&loop, plan->phase_ev[1], plan->phase_ev[2]);
+    cudaEventElapsedTime(&post, plan->phase_ev[2], plan->phase_ev[3]);
+    os << "\"phase_ms\":{\"pre\":" << pre << ",\"slice_loop\":" << loop << ",\"post\":" << post << "},";
+  }
+  os << "\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices
      << ",\"restricted_launches\":" << plan->rr_launches << ",\"graph_captures\":" << plan->n_captures
      << ",\"graph_replays\":" << plan->n_replays << ",\"ops\":[";
   bool first = true;
@@ -1275,7 +1292,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
 
 int tsb_plan_set_timing(tsb_plan* plan, int enabled) {
   if (!plan) { tsb::set_error("null argument"); return TSB_ERR_INVALID; }
-  plan->timing = enabled != 0;
+  plan->timing = enabled < 0 ? 0 : enabled > 2 ? 1 : enabled;
   return TSB_OK;
 }
 
@@ -1317,8 +1334,17 @@ MaskPlan make_mask(const tsb_plan& P, int64_t slice_begin, int64_t slice_end) {
 // launches depends only on (plan, base, out, slice range) — and on the leaf pointers where P.bakes_leaf_ptrs — so
 // the same call can run directly or under stream capture.  The pointer table d_ptrs is uploaded by the caller.
 void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs, int64_t slice_begin, int64_t slice_end,
-                       void* out, const MaskPlan& mask, cudaStream_t stream, bool timing, int n_side_max) {
+                       void* out, const MaskPlan& mask, cudaStream_t stream, int timing_mode, int n_side_max) {
   tsb_ctx* ctx = P.ctx;
+  const bool timing = timing_mode == 1;
+  const bool phases = timing_mode == 2;
+  auto phase_mark = [&](int i) {
+    if (!phases) return;
+    if (!P.phase_ev[i]) TSB_CUDA(cudaEventCreate(&P.phase_ev[i]));
+    TSB_CUDA(cudaEventRecord(P.phase_ev[i], stream));
+  };
+  P.phase_valid = false;
+  phase_mark(0);
   if (timing && P.ev.size() < 2 * P.ops.size() + 2) {
     size_t old = P.ev.size();
     P.ev.resize(2 * P.ops.size() + 2);
@@ -1451,6 +1477,7 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
   }
   run_schedule(P.schedule);
   P.rr_nfixed = 0;
+  phase_mark(1);
   // per-slice part
   if (!P.sliced.empty()) {
     for (int64_t sid = slice_begin; sid < slice_end; sid++) {
@@ -1478,6 +1505,7 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
       }
     }
   }
+  phase_mark(2);
   run_schedule(P.post_schedule);
   if (P.mask_root) {
     // out[o] = sum over sliced-wire combinations s in [slice_begin, slice_end) of root[s, o]
@@ -1504,6 +1532,8 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
     rewire_impl(ctx, base + r.offset, (int)axes.size(), ext.data(), nullptr, r.dtype, out, (int)ports.size(),
                 ports.data(), r.dtype, false, false, stream);
   }
+  phase_mark(3);
+  P.phase_valid = phases;
 }
 
 // pointer table for the batched small ops: [arena, out, leaves...]; uploaded only when it changed
@@ -1522,8 +1552,9 @@ void upload_ptrs(tsb_plan& P, uint8_t* base, void* out, const void* const* leaf_
 #ifndef TSB_HOST_EMU
 void destroy_graph_entry(tsb_plan& P, tsb_plan::GraphEntry& e) {
   if (e.exec) cudaGraphExecDestroy(e.exec);
-  for (void* p : e.held) P.ctx->arena.release(p);
-  e.held.clear();
+  for (void* p : e.held.owned) P.ctx->arena.release(p);
+  e.held.owned.clear();
+  e.held.free.clear();
   e.exec = nullptr;
 }
 
@@ -1567,19 +1598,20 @@ bool execute_as_graph(tsb_plan& P, const void* const* leaf_ptrs, int64_t slice_b
     tsb_plan::GraphEntry e;
     const int64_t launches0 = ctx->launches;
     cudaGraph_t graph = nullptr;
-    bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (!P.cap_stream && cudaStreamCreateWithFlags(&P.cap_stream, cudaStreamNonBlocking) != cudaSuccess) P.cap_stream = nullptr;
+    bool ok = P.cap_stream && cudaStreamBeginCapture(P.cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
       ctx->hold = &e.held;
       ctx->cap_counts = &e.kcount;
       try {
-        enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, own_result ? P.gres : out, mask, stream,
-                          false, graph_streams);
+        enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, own_result ? P.gres : out, mask,
+                          P.cap_stream, false, graph_streams);
       } catch (const tsb::Error&) {
         ok = false;
       }
       ctx->hold = nullptr;
       ctx->cap_counts = nullptr;
-      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr) ok = false;
+      if (cudaStreamEndCapture(P.cap_stream, &graph) != cudaSuccess || graph == nullptr) ok = false;
     }
     if (ok && cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) ok = false;
     if (graph) cudaGraphDestroy(graph);
@@ -1653,7 +1685,7 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       // the caller is capturing this stream into its own graph: the launches must keep their memory for as long
       // as the plan lives (the caller's replays use the same addresses), and no event may be recorded
       if (!P.gblock) P.gblock = ctx->arena.alloc((size_t)std::max<int64_t>(P.info.peak_bytes, 256));
-      static std::vector<void*> forever;   // temporaries of caller-captured launches are never recycled
+      static tsb::HeldBlocks forever;      // temporaries of caller-captured launches stay theirs (recycled in capture order)
       ctx->hold = &forever;
       try {
         upload_ptrs(P, (uint8_t*)P.gblock, out, leaf_ptrs, stream);
@@ -1692,7 +1724,9 @@ int tsb_plan_destroy(tsb_plan* plan) {
     } catch (...) {
     }
     if (plan->done_ev) cudaEventDestroy(plan->done_ev);
+    if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     for (auto e : plan->ev) cudaEventDestroy(e);
+    for (auto e : plan->phase_ev) if (e) cudaEventDestroy(e);
     for (auto e : plan->side_ev) cudaEventDestroy(e);
     for (auto st : plan->side) cudaStreamDestroy(st);
     if (plan->d_small_ops) cudaFree(plan->d_small_ops);

@@ -536,7 +536,9 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
     monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")       # fuse consecutive packed steps whatever their size ...
     monkeypatch.setenv("TSB_FUSE_MAX_K", str(fuse_k))  # ... up to this many summed wires per launch (-1: never)
     monkeypatch.setenv("TSB_FUSE_PAIR", str(pair))     # pair wires of k_merge_bits_f (-1: k_merge_bits_n only)
-    monkeypatch.setenv("TSB_FUSE_LANES", "0" if (seed, pair) == (6, 1) else "1")   # chosen lane wires: on except in two cases
+    tile = seed in (2, 4)                              # tile wires chosen by operand footprint (TSB_FUSE_TILE) ...
+    monkeypatch.setenv("TSB_FUSE_TILE", "1" if tile else "0")
+    monkeypatch.setenv("TSB_FUSE_LANES", "0" if (seed, pair) == (6, 1) or tile else "1")   # ... or lane wires by wavefronts
     cnf = CNFInstance.random(3, n, m, rng=seed)
     flat, net0 = _network_and_leaves(cnf.inputs(None) >> cnf.diagram())
     outs = tuple(int(v) for v in np.linspace(0, n - 1, n_out).astype(int))

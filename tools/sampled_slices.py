@@ -127,8 +127,8 @@ def main():
     if rank == 0:
         peak = 6650.0
         try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peak = float(json.load(f)["hbm_gbs"])
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peak = float(json.load(fh)["hbm_gbs"])
         except Exception:
             pass
         alg = plan.info["alg_bytes_shared"] + plan.info["alg_bytes_per_slice"] * n
