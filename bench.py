@@ -210,6 +210,141 @@ def run_reference(args) -> None:
     print(json.dumps(line))
 
 
+def micro_rooflines(hbm: float, hbm_src: str) -> dict:
+    """North-star kernels that the n=50 plan does not exercise, on the shapes of the multiplier plan (config 5), timed
+    with CUDA events after warm-up on tensors larger than L2: the bit-permutation transposes (HBM roofline, algorithmic
+    bytes = 2 x tensor bytes) and the tcgen05 int8 GEMM (tensor roofline, ops = 2 x 2^(b+m+n+k))."""
+    import numpy as np
+    import torch
+
+    from tensorsat_b200 import _native
+
+    def time_op(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = 30
+    src = (torch.rand(1 << r, device="cuda", generator=g) < 0.5).to(torch.uint8)
+    dst = torch.empty_like(src)
+    rng = np.random.default_rng(0)
+    # the transposes around a GEMM-lowered step gather the summed wires to the low axes; plus seeded random
+    # permutations of all 30 axes
+    cases = {"gemm_operand_gather (every second axis pulled to the low end)": [i for i in range(r) if i % 2 == 0] + [i for i in range(r) if i % 2 == 1],
+             "rotate_by_13": list(range(13, r)) + list(range(13))}
+    for i in range(3):
+        cases[f"random_{i}"] = [int(x) for x in rng.permutation(r)]
+    perm_rows = []
+    for name, perm in cases.items():
+        ms = time_op(lambda: _native.permute(src, dst, [2] * r, perm, 1), 10)
+        perm_rows.append({"case": name, "ms": ms, "GBps": 2.0 * (1 << r) / (ms * 1e-3) / 1e9})
+    gb = sorted(x["GBps"] for x in perm_rows)
+    med = gb[len(gb) // 2]
+    permute = {"bound": "hbm", "kernel": "k_permute<G> / k_permute_t4 on 2^30-byte tensors (rank 30, u8)", "achieved": med, "peak": hbm,
+               "unit": "GB/s", "frac": med / hbm, "traffic": 2.0 * (1 << r), "peak_source": hbm_src, "alg_bytes_per_launch": 2.0 * (1 << r),
+               "achieved_is": "median over the cases", "min_frac": gb[0] / hbm, "max_frac": gb[-1] / hbm, "cases": perm_rows}
+    del dst
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    nominal_i8 = 4500.0
+    rows = []
+    for (b, m, n, k) in [(2, 13, 15, 13), (0, 13, 13, 13), (4, 11, 11, 11)]:   # first: the largest step of the multiplier plan
+        A = src[: 1 << (b + m + k)]
+        B = src[: 1 << (b + n + k)]
+        for mode, dt in ((0, torch.uint8), (1, torch.int32)):
+            C = torch.empty(1 << (b + m + n), dtype=dt, device="cuda")
+            ms = time_op(lambda: _native.gemm_u8(A, B, C, b, m, n, k, mode), 5)
+            ops = 2.0 * 2.0 ** (b + m + n + k)
+            rows.append({"b": b, "m": m, "n": n, "k": k, "epilogue": "clamp count>0 (u8)" if mode == 0 else "exact (s32)", "ms": ms,
+                         "TOPs": ops / (ms * 1e-3) / 1e12})
+            del C
+    top = rows[0]["TOPs"]
+    gemm = {"bound": "tensor", "kernel": "k_gemm_i8 (tcgen05.mma kind::i8, TMEM accumulators, TMA operands), largest GEMM step of the multiplier plan, boolean epilogue",
+            "achieved": top, "peak": nominal_i8, "unit": "TOP/s", "frac": top / nominal_i8, "traffic": None,
+            "peak_source": ("nominal dense int8 of B200 (4.5 Pop/s = 2 x the nominal 2.25 PF/s bf16); MEASURED_PEAKS.json has no int8 entry, "
+                            f"its measured bf16 burst is {bf16:.0f} TF/s, i.e. 2 x measured bf16 = {2 * bf16:.0f} TOP/s"),
+            "frac_of_2x_measured_bf16": top / (2 * bf16), "alg_ops_per_launch": 2.0 * 2.0 ** (2 + 13 + 15 + 13), "cases": rows}
+    return {"permute": permute, "gemm": gemm}
+
+
+def c4_subcube_leg(world: int, rank: int, keep: int, steps: int) -> dict | None:
+    """BASELINE config 4 (random 3-SAT n=200 m=852 seed 0, the north-star's sliced multi-GPU instance) on a SAMPLED
+    sub-cube: the tree (width 136) is sliced to 2^30-entry intermediates = 2^106 slices; all but `keep` sliced
+    wires are pinned along a committed model of the instance, the remaining 2^keep slices are split over the
+    ranks in contiguous blocks and combined by one all-reduce (max).  The sub-cube contains the model, so its
+    exact answer is SAT (checked)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tensorsat_b200 import _native
+    from tensorsat_b200.distributed import all_reduce_result, slice_block
+    from tensorsat_b200.planner import subcube
+
+    if not os.path.exists(subcube.path_of("c4")):
+        return None
+    f = subcube.load("c4")
+    sub, subleaves, asg = f.subcube(keep)
+    net = sub.network
+    plan = _native.Plan(net.inputs, net.output, net.size_dict, sub.ssa_path, sub.sliced_wires, mode=_native.MODE_SAT)
+    leaves = [_native.upload(np.ascontiguousarray(t, dtype=np.uint8)) for t in subleaves]
+    out = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
+    n = int(plan.info["n_slices"])
+    lo, hi = slice_block(n, rank, world)
+
+    def step() -> None:
+        plan.execute(leaves, out, lo, hi)
+        if world > 1:
+            all_reduce_result(out, _native.MODE_SAT)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    result = int(out.cpu().numpy().reshape(-1)[0])
+    info = plan.info
+    alg = info["alg_bytes_shared"] + info["alg_bytes_per_slice"] * n
+    res = {
+        "workload": (f"{f.description}; elimination-order tree (width {f.extra['tree_log2_width']:.0f}) sliced to 2^30-entry "
+                     f"intermediates = 2^{f.extra['n_sliced']} slices of the full instance; SAMPLED: {len(asg)} sliced wires pinned "
+                     f"along a committed model, the other 2^{keep} = {n} slices executed"),
+        "value": ms * 1e-3, "unit": "s", "ms_per_slice": ms / max(hi - lo, 1), "n_slices": n, "slices_per_rank": int(hi - lo),
+        "steps": steps, "scaling": "strong", "result": "SAT" if result else "UNSAT", "expected": "SAT (the sub-cube contains the model)",
+        "kernels_once": int(info["n_kernels_shared"]), "kernels_per_slice": int(info["n_kernels_per_slice"]),
+        "alg_bytes_moved_per_contraction": alg, "alg_GBps": alg / (ms * 1e-3) / 1e9,
+        "peak_arena_bytes": int(info["peak_bytes"]), "timing": "CUDA events per contraction incl. the all-reduce, max over ranks",
+    }
+    assert result == 1, "the sampled sub-cube of config 4 contains a model: the contraction must say SAT"
+    plan.close()
+    return res
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

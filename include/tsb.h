@@ -258,6 +258,58 @@ int tsb_plan_set_timing(tsb_plan* plan, int enabled);
 int tsb_plan_timing_json(tsb_plan* plan, char* buf, size_t cap, size_t* needed);
 int tsb_plan_destroy(tsb_plan* plan);
 
+/* ---- front end: DIMACS / clause lists -> flat relation network -> contraction tree -> plan, all on the host and without
+ *      Python diagram objects.  Replaces, for CNF inputs, CNFInstance.from_dimacs / inputs / diagram
+ *      (tensorsat/lib/sat.py:80-100,165-206,248-262), `>>` + flatten (tensorsat/diagrams.py:387-461,1452-1481) and the
+ *      tree search the reference delegates to cotengra (tensorsat/contractions/cotengra.py:78-85).  Wire and slot
+ *      numbering are exactly those of `(cnf.inputs(x) >> cnf.diagram()).flatten()`. ------------------------------- */
+typedef struct tsb_network tsb_network;
+typedef struct tsb_tree tsb_tree;
+typedef enum {               /* the gate relations of tensorsat/lib/bincirc.py:42-73 */
+  TSB_LEAF_BIT_0 = 0,        /* [1, 0] */
+  TSB_LEAF_BIT_1 = 1,        /* [0, 1] */
+  TSB_LEAF_BIT_UNK = 2,      /* [1, 1] */
+  TSB_LEAF_NOT = 3,          /* [in][out], out = !in */
+  TSB_LEAF_OR = 4            /* [a][b][out], out = a | b */
+} tsb_leaf_kind;
+typedef struct {
+  int32_t n_vars, n_clauses, n_leaves, n_wires, n_out;
+  int32_t reserved;
+  int64_t total_leaf_rank;   /* length of the concatenated leaf wire lists */
+  int64_t total_leaf_bytes;  /* bytes of all leaf tensors (one byte per entry) */
+} tsb_network_info_t;
+typedef struct {
+  int32_t n_leaves, n_steps, n_sliced, reserved;
+  double log2_width;           /* largest intermediate of one slice, log2 entries */
+  double log2_width_unsliced;
+  double log2_ops, log2_write; /* whole job (all slices): the cost model cotengra reports */
+} tsb_tree_info_t;
+
+/* inputs: NULL = no input boxes (the variables stay open: all-solutions tensor), else one character per variable,
+ * '0' / '1' fix it, '?' leaves it unknown (bit_unk box). */
+int tsb_network_from_clauses(int32_t n_vars, int32_t n_clauses, const int32_t* clause_sizes, const int32_t* literals,
+                             const char* inputs, tsb_network** net);
+int tsb_network_from_dimacs(const char* dimacs_text, const char* inputs, tsb_network** net);
+/* Swap the input boxes (assignment search: same wiring, same tree, same plan). */
+int tsb_network_set_inputs(tsb_network* net, const char* inputs);
+int tsb_network_info(const tsb_network* net, tsb_network_info_t* info);
+/* Caller-allocated arrays (any may be NULL): leaf_ranks / leaf_kinds [n_leaves], leaf_wires [total_leaf_rank],
+ * out_wires [n_out]. */
+int tsb_network_arrays(const tsb_network* net, int32_t* leaf_ranks, int32_t* leaf_wires, int32_t* leaf_kinds,
+                       int32_t* out_wires);
+/* The 0/1 leaf tensors, C order, concatenated in slot order into buf [total_leaf_bytes]; offsets [n_leaves] optional. */
+int tsb_network_leaf_tensors(const tsb_network* net, uint8_t* buf, int64_t* offsets);
+int tsb_network_destroy(tsb_network* net);
+/* Best of `trials` elimination-order trees (min-fill / min-degree, trials >= 2 randomised from `seed`), then sliced
+ * until the largest intermediate has at most 2^target_log2_size entries (<= 0: no slicing). */
+int tsb_tree_search(const tsb_network* net, int32_t trials, uint64_t seed, double target_log2_size, tsb_tree** tree);
+int tsb_tree_info(const tsb_tree* tree, tsb_tree_info_t* info);
+int tsb_tree_arrays(const tsb_tree* tree, int32_t* ssa_path /* [2 * n_steps] */, int32_t* sliced_wires /* [n_sliced] */);
+int tsb_tree_destroy(tsb_tree* tree);
+/* tsb_plan_create on the network and tree above (counting mode: only the variables are free wires). */
+int tsb_plan_create_from_tree(tsb_ctx* ctx, const tsb_network* net, const tsb_tree* tree, int32_t mode, int32_t batch_log2,
+                              uint32_t flags, tsb_plan** plan);
+
 /* ---- micro-benchmark / test hooks for the individual kernels ------------------------------ */
 /* C[b][m][n] = sum_k A[b][m][k] * B[b][n][k], u8 operands, tcgen05 kind::i8 with s32 TMEM
  * accumulators.  out_dtype u8: clamp (acc != 0) when mode is TSB_SAT, else low byte;

@@ -89,7 +89,9 @@ EXPORTS = [
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
     "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_all_binary", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
     "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",
-    "tsb_plan_destroy", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
+    "tsb_plan_destroy", "tsb_network_from_clauses", "tsb_network_from_dimacs", "tsb_network_set_inputs", "tsb_network_info",
+    "tsb_network_arrays", "tsb_network_leaf_tensors", "tsb_network_destroy", "tsb_tree_search", "tsb_tree_info",
+    "tsb_tree_arrays", "tsb_tree_destroy", "tsb_plan_create_from_tree", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
 ]
 """Every symbol include/tsb.h declares (checked by tests/test_abi.py)."""
 
@@ -376,6 +378,18 @@ class Plan:
         info = PlanInfo()
         _check(lib().tsb_plan_info(self._h, C.byref(info)))
         self.info = {f: getattr(info, f) for f, _ in PlanInfo._fields_}
+
+    @classmethod
+    def from_handle(cls, handle: C.c_void_p, n_leaves: int, mode: int) -> "Plan":
+        """Wraps a ``tsb_plan*`` created elsewhere (``tsb_plan_create_from_tree``)."""
+        self = cls.__new__(cls)
+        self._h = handle
+        self.mode = int(mode)
+        self.n_leaves = int(n_leaves)
+        info = PlanInfo()
+        _check(lib().tsb_plan_info(self._h, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in PlanInfo._fields_}
+        return self
 
     def execute(self, leaves: Sequence[Any], out: Any, slice_begin: int = 0, slice_end: int | None = None) -> None:
         if len(leaves) != self.n_leaves:

@@ -703,7 +703,8 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
   d = BitsFDesc{};
   d.R = R; d.kbits = KB; d.n_ops = n; d.n_pair = NP;
   const int vr = vb - NP;  // reduced vector-index bits
-  d.tile_bits = std::min(vr, std::min(kMergeTileBits, std::max(8, vr - 10)));
+  static const int tile_env = [] { const char* e = getenv("TSB_BITSF_TILE_BITS"); return e ? atoi(e) : kMergeTileBits; }();  // A/B knob
+  d.tile_bits = std::min(vr, std::min(std::min(kMergeTileBits, std::max(tile_env, 6)), std::max(8, vr - 10)));
   d.n_vec = int64_t(1) << vr;
   for (int g = 0; g < 4; g++) {
     uint32_t w = 0;

@@ -33,7 +33,14 @@ void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* pt
                                                  : bits_f_kernel_small(d.n_ops, d.kbits, d.masks, d.n_pair);
   TSB_CHECK(k != nullptr, TSB_ERR_INVALID, "internal: no factored merge kernel for masks %d", d.masks);
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (d.n_pair ? 2 : 3)));
+  // tuning knobs (A/B runs): persistent CTAs per SM, shared-memory carve-out (percent; the rest of the 256 KB is L1)
+  static const int ctas_env = [] { const char* e = getenv("TSB_BITSF_CTAS"); return e ? atoi(e) : 0; }();
+  const int per_sm = ctas_env > 0 ? ctas_env : (d.n_pair ? 2 : 3);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm));
+#ifndef TSB_HOST_EMU
+  static const int carve_env = [] { const char* e = getenv("TSB_BITSF_CARVEOUT"); return e ? atoi(e) : -1; }();
+  if (carve_env >= 0) cudaFuncSetAttribute((const void*)k, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env);
+#endif
   TSB_LAUNCH_PDL(k, dim3(grid), dim3(kBitsFThreads), 0, stream, d, pp, (uint4*)o);
   ctx->note("k_merge_bits_f");
   TSB_CUDA(cudaGetLastError());

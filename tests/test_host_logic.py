@@ -200,3 +200,22 @@ def test_subcube_plan_files_are_consistent():
     sub, subleaves, asg = f.subcube(2)
     for ws, t in zip(sub.network.inputs, subleaves):
         assert t.ndim == len(ws)
+
+
+def test_bench_script_is_whole():
+    """bench.py refers only to functions it defines (a cheap guard: the driver runs it unattended)."""
+    import ast
+
+    src = open(os.path.join(os.path.dirname(GOLDEN), "..", "bench.py")).read()
+    tree = ast.parse(src)
+    defined = {n.name for n in tree.body if isinstance(n, ast.FunctionDef)} | {n.name for n in tree.body if isinstance(n, ast.ClassDef)}
+    called = {n.func.id for n in ast.walk(tree) if isinstance(n, ast.Call) and isinstance(n.func, ast.Name)}
+    import builtins
+
+    local_names = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+    local_names |= {a.arg for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) for a in n.args.args}
+    local_names |= {n.name for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)}
+    missing = {c for c in called if c not in defined and c not in local_names and not hasattr(builtins, c)}
+    assert not missing, missing
+    for fn in ("load_tree", "cpu_sample", "run_reference", "micro_rooflines", "c4_subcube_leg", "main"):
+        assert fn in defined
