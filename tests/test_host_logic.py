@@ -215,6 +215,7 @@ def test_bench_script_is_whole():
     local_names = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
     local_names |= {a.arg for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) for a in n.args.args}
     local_names |= {n.name for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)}
+    local_names |= {(a.asname or a.name).split(".")[0] for n in ast.walk(tree) if isinstance(n, (ast.Import, ast.ImportFrom)) for a in n.names}
     missing = {c for c in called if c not in defined and c not in local_names and not hasattr(builtins, c)}
     assert not missing, missing
     for fn in ("load_tree", "cpu_sample", "run_reference", "micro_rooflines", "c4_subcube_leg", "main"):
