@@ -8,7 +8,7 @@
 
 namespace tsb {
 
-using BitsFKernel = void (*)(const BitsFDesc, const BitsNPtrs, uint4*);
+using BitsFKernel = void (*)(const BitsFDesc, const BitsNPtrs, uint4*, const uint32_t*);
 
 constexpr bool bits_f_sorted(int masks, int kb, int nops) {
   for (int o = 0; o + 1 < nops; o++)
@@ -39,11 +39,22 @@ inline BitsFKernel bits_f_kernel(int masks, int n_pair) {
   return n_pair == 0 ? bits_f_lookup<NOPS, KB, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 1>(masks, seq);
 }
 
+// the four-vector (two pair wires, Gray order) instantiations: one translation unit per group that has them
+template <int NOPS, int KB>
+inline BitsFKernel bits_f_kernel_np2(int masks) {
+  constexpr int N = 1 << (KB * NOPS);
+  return bits_f_lookup<NOPS, KB, 2>(masks, std::make_integer_sequence<int, N>{});
+}
+
 }  // namespace
 
 // one per translation unit
 BitsFKernel bits_f_kernel_4_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_3_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_small(int nops, int kb, int masks, int n_pair);  // everything else
+BitsFKernel bits_f_kernel_np2_4_2(int masks);   // n_pair = 2 exists for the (4, 2), (3, 2), (4, 1), (3, 1) groups only
+BitsFKernel bits_f_kernel_np2_3_2(int masks);
+BitsFKernel bits_f_kernel_np2_x_1(int nops, int masks);
+inline bool bits_f_has_np2(int nops, int kb) { return (nops == 3 || nops == 4) && (kb == 1 || kb == 2); }
 
 }  // namespace tsb

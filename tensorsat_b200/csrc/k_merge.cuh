@@ -101,7 +101,7 @@ struct BitsNPtrs {
 // descriptor of the factored fused merge (k_merge_bits_f.cuh): summed-wire masks known at compile time,
 // optionally one "pair" output wire handled per thread so that operands that do not hold it are fetched once
 constexpr int kBitsFMaxKB = 2;
-constexpr int kBitsFMaxPair = 1;
+constexpr int kBitsFMaxPair = 2;
 
 struct BitsFOperand {
   BitRuns lo, hi;   // reduced vector-in-tile index / reduced tile index -> operand offset (entries)

@@ -639,7 +639,7 @@ struct BitsFArgs {
 };
 
 inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
-                                  int n_top_excluded = 0, bool choose_lanes = false, bool choose_tile = false) {
+                                  int n_top_excluded = 0, bool choose_lanes = false, int choose_tile = 0) {
   BitsFArgs m;
   const int R = (int)out_bits.size(), n = (int)operands.size();
   if (R < 7 || R > 62 || n < 2 || n > kBitsMaxOps || has_dups(out_bits)) return m;
@@ -683,7 +683,9 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
   std::vector<int> pair_pos;
   std::vector<int> loads(n);
   for (int o = 0; o < n; o++) loads[o] = 1 << __builtin_popcount((unsigned)kmask[o]);
-  while ((int)pair_pos.size() < std::min(max_pair, kBitsFMaxPair) && vb - (int)pair_pos.size() > 8) {
+  // two pair wires (four vectors per work item) exist for the three- and four-operand groups with summed wires
+  const int pair_cap = std::min(std::min(max_pair, kBitsFMaxPair), ((n == 3 || n == 4) && (KB == 1 || KB == 2)) ? 2 : 1);
+  while ((int)pair_pos.size() < pair_cap && vb - (int)pair_pos.size() > 8) {
     int best = -1, best_score = 0;
     for (int j = 8; j < R - n_top_excluded; j++) {  // the leading (sliced) wires stay index bits: sub-range launches
       if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
@@ -698,6 +700,23 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
       if (lp[o].count(out_bits[R - 1 - best])) loads[o] *= 2;
   }
   std::sort(pair_pos.begin(), pair_pos.end());
+  if (pair_pos.size() == 2) {
+    // Two pair wires: exhaustive choice.  In the Gray walk 0, 1, 3, 2 pair wire [0] flips twice, [1] once: per four
+    // vectors an operand is fetched once if it holds neither, twice if only [1], three times if only [0], four
+    // times if both.  Pick the (ordered) pair of output wires with the fewest fetches.
+    static const int times[4] = {1, 3, 2, 4};
+    long best = -1;
+    for (int j0 = 8; j0 < R - n_top_excluded; j0++)
+      for (int j1 = 8; j1 < R - n_top_excluded; j1++) {
+        if (j0 == j1) continue;
+        long cost = 0;
+        for (int o = 0; o < n; o++) {
+          const int held = (lp[o].count(out_bits[R - 1 - j0]) ? 1 : 0) | (lp[o].count(out_bits[R - 1 - j1]) ? 2 : 0);
+          cost += (1L << __builtin_popcount((unsigned)kmask[o])) * times[held];
+        }
+        if (best < 0 || cost < best) { best = cost; pair_pos[0] = j0; pair_pos[1] = j1; }
+      }
+  }
   const int NP = (int)pair_pos.size();
   BitsFDesc& d = m.d;
   d = BitsFDesc{};
@@ -793,6 +812,16 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
     std::vector<int> cand;
     for (int j = 8; j < R - n_top_excluded; j++)
       if (std::find(pair_pos.begin(), pair_pos.end(), j) == pair_pos.end()) cand.push_back(j);
+    if (choose_tile == 2) {
+      // the 32 lanes of a warp keep the lowest output wires (coalesced 16-byte fetches and stores); only the
+      // remaining tile wires are chosen by footprint
+      while ((int)lanes.size() < 4 && !cand.empty()) {
+        const int j = cand.front();
+        cand.erase(cand.begin());
+        lanes.push_back(j);
+        for (int o = 0; o < n; o++) if (lp[o].count(out_bits[R - 1 - j])) fp[o] *= 2;
+      }
+    }
     while ((int)lanes.size() < d.tile_bits - 1 && !cand.empty()) {
       int best = -1;
       double best_cost = 0;
@@ -836,7 +865,8 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
 }
 
 void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
-                         cudaStream_t s);
+                         cudaStream_t s, const uint32_t* tables = nullptr);
+std::vector<uint32_t> bits_f_tables(const BitsFDesc& d);
 
 void launch_merge_bits_n(tsb_ctx* ctx, const BitsNDesc& d, const void* const* ptrs, const uint64_t* bitoffs, void* o,
                          cudaStream_t s);

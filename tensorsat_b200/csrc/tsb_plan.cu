@@ -81,6 +81,7 @@ struct POp {
   long wf_chosen = 0, wf_default = 0;     // modelled L1 wavefronts per work item (make_bits_f_desc)
   double launch_entries = 0;              // fused step: entries the launch must read and write (operands + result)
   bool use_f = false;
+  int64_t tab_off = -1;                   // use_f: offset (uint32 units) of this step's offset tables in the plan's d_tabs
   int n_operands() const { return kind == OP_STEP ? 2 + (int)xn.size() : 1; }
   std::vector<int> all_operands() const { std::vector<int> v{lhs, rhs}; v.insert(v.end(), xn.begin(), xn.end()); return v; }
   int operand(int j) const { return j == 0 ? lhs : j == 1 ? rhs : xn[j - 2]; }
@@ -150,6 +151,7 @@ struct tsb_plan {
   std::vector<int> slice_ops;          // per-slice ops, in order
   std::vector<SmallOp> small_ops;      // host copy
   SmallOp* d_small_ops = nullptr;
+  uint32_t* d_tabs = nullptr;          // offset tables of the factored fused steps, computed once (bits_f_tables)
   void** d_ptrs = nullptr;             // device pointer table: [arena, out, leaf 0, leaf 1, ...]
   std::vector<void*> h_ptrs;           // host copy of the table (pageable: the async copy stages it)
   bool mask_root = false;              // root keeps the sliced wires; a final masked sum selects the executed slices
@@ -782,7 +784,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
             if (P.nodes[y].shared)
               for (auto w : P.nodes[y].slab) n_slab_bits += ilog2(P.wext[w]);
             BitsFArgs f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, env_or("TSB_FUSE_LANES", 0.0) != 0.0,
-                                           env_or("TSB_FUSE_TILE", 0.0) != 0.0);
+                                           (int)env_or("TSB_FUSE_TILE", 0.0));
             if (!f.ok && env_or("TSB_FUSE_TILE", 0.0) != 0.0)   // too many bit runs for the tables: plain order
               f = make_bits_f_desc(ol, ob, kFusePair, n_slab_bits, false, false);
             if (f.ok) { op.fd = f.d; op.use_f = true; op.wf_chosen = f.wf_chosen; op.wf_default = f.wf_default; }
@@ -999,6 +1001,22 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     if (op.kind == OP_STEP) mx = std::max(mx, ilog2(std::max<int64_t>(1, prod_ext(op.ow, P.wext))));
   }
   P.info.log2_max_tensor = mx;
+  {
+    // per-tile offset tables of the factored fused steps: they depend on the descriptor only, so they are deposited
+    // once here instead of by every CTA of every launch (a sixth of the slice loop on the n=50 bench)
+    static const bool pre_tab = [] { const char* e = getenv("TSB_BITSF_TABLES"); return !(e && e[0] == '0'); }();
+    std::vector<uint32_t> all;
+    for (auto& op : P.ops) {
+      if (!pre_tab || !op.use_f) continue;
+      op.tab_off = (int64_t)all.size();
+      const std::vector<uint32_t> t = bits_f_tables(op.fd);
+      all.insert(all.end(), t.begin(), t.end());
+    }
+    if (!all.empty()) {
+      TSB_CUDA(cudaMalloc((void**)&P.d_tabs, all.size() * sizeof(uint32_t)));
+      TSB_CUDA(cudaMemcpy(P.d_tabs, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+  }
   for (auto& op : P.ops)
     if (op.kind == OP_LEAF && !op.small) P.bakes_leaf_ptrs = true;
   if (P.n_leaves == 1) P.bakes_leaf_ptrs = true;
@@ -1111,9 +1129,9 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
       BitsFDesc d = op.fd;
       d.n_vec >>= fo;
       P.rr_launches++;
-      launch_merge_bits_f(ctx, d, ptrs, offs, base + o.offset + (oo >> 3), stream);
+      launch_merge_bits_f(ctx, d, ptrs, offs, base + o.offset + (oo >> 3), stream, op.tab_off >= 0 ? P.d_tabs + op.tab_off : nullptr);
     } else if (op.use_f) {
-      launch_merge_bits_f(ctx, op.fd, ptrs, offs, po_bits, stream);
+      launch_merge_bits_f(ctx, op.fd, ptrs, offs, po_bits, stream, op.tab_off >= 0 ? P.d_tabs + op.tab_off : nullptr);
     } else {
       launch_merge_bits_n(ctx, op.nd, ptrs, offs, po_bits, stream);
     }
@@ -1232,8 +1250,15 @@ static int fetches_x4(const POp& op) {
   if (op.xn.empty()) return 0;
   if (!op.use_f) return 4 * op.nd.n_ops << op.nd.kbits;
   int n = 0;
-  for (int s = 0; s < op.fd.n_ops; s++)
-    n += (4 >> op.fd.n_pair) << (__builtin_popcount((unsigned)op.fd.op[s].kmask) + __builtin_popcount((unsigned)op.fd.op[s].held));
+  for (int s = 0; s < op.fd.n_ops; s++) {
+    const int kk = 1 << __builtin_popcount((unsigned)op.fd.op[s].kmask);
+    if (op.fd.n_pair == 2) {   // Gray walk over four vectors: fetched 1 / 3 / 2 / 4 times for held = none / [0] / [1] / both
+      static const int times[4] = {1, 3, 2, 4};
+      n += kk * times[op.fd.op[s].held & 3];
+    } else {
+      n += ((4 >> op.fd.n_pair) * kk) << __builtin_popcount((unsigned)op.fd.op[s].held);
+    }
+  }
   return n;
 }
 
@@ -1730,6 +1755,7 @@ int tsb_plan_destroy(tsb_plan* plan) {
     for (auto e : plan->side_ev) cudaEventDestroy(e);
     for (auto st : plan->side) cudaStreamDestroy(st);
     if (plan->d_small_ops) cudaFree(plan->d_small_ops);
+    if (plan->d_tabs) cudaFree(plan->d_tabs);
     if (plan->d_ptrs) cudaFree(plan->d_ptrs);
     tsb::ctx_unref(plan->ctx);
     delete plan;
