@@ -442,15 +442,11 @@ def main() -> None:
     # ---- end to end through the public API with HOST leaf buffers
     leaves_host = [b.tensor for b in diagram.boxes]
     for _ in range(2):
-        contraction.contract_from_host(leaves_host, (lo, hi))
+        contraction.contract_from_host(leaves_host, (lo, hi), all_reduce=world > 1)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = contraction.contract_from_host(leaves_host, (lo, hi))
-        if world > 1:
-            r = torch.from_numpy(res.reshape(-1).copy()).cuda()
-            all_reduce_result(r, contraction.mode)
-            res = r.cpu().numpy()
+        res = contraction.contract_from_host(leaves_host, (lo, hi), all_reduce=world > 1)
     sync_all()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if world > 1:

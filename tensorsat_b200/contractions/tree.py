@@ -152,10 +152,13 @@ class TreeContraction(Contraction):
         plan.execute(leaves, out, lo, hi)
         return out
 
-    def contract_from_host(self, leaves: Sequence[Any], slice_range: tuple[int, int] | None = None) -> Any:
+    def contract_from_host(self, leaves: Sequence[Any], slice_range: tuple[int, int] | None = None, *,
+                           group: Any = None, all_reduce: bool = False) -> Any:
         """End-to-end call on HOST buffers: ``leaves`` are the uint8 0/1 numpy arrays of the boxes (in
         slot order).  They are packed into one pinned staging buffer, copied to the device with one
-        H2D transfer, contracted, and the result is read back (D2H) as a numpy array."""
+        H2D transfer, contracted, and the result is read back (D2H) as a numpy array.  With ``all_reduce`` the
+        partial result of this rank's ``slice_range`` is combined across the ranks of ``group`` on the device
+        (one collective: max / sum) before the read-back."""
         import numpy as np
         import torch
 
@@ -197,6 +200,10 @@ class TreeContraction(Contraction):
         out = _native.empty(plan.info["out_numel"], self.mode)
         lo, hi = (0, plan.info["n_slices"]) if slice_range is None else slice_range
         plan.execute_ptrs(ptrs, out.data_ptr(), lo, hi)
+        if all_reduce:
+            from ..distributed import all_reduce_result
+
+            all_reduce_result(out, self.mode, group)
         res.copy_(out, non_blocking=False)
         # the plan contracts onto the DISTINCT output wires; repeated output wires tie axes to a diagonal
         # (what contract() does with _rewire; simple.py:287-289)

@@ -39,6 +39,13 @@ part = TreeContraction(CudaCountRel, d.wiring, tree=tree, wire_is_free=free).con
 t = torch.tensor([int(part)])
 dist.all_reduce(t)
 assert int(t) == int(brute.sum())
+# the end-to-end entry point on host leaves, combined on the device before the read-back (what bench.py's e2e times)
+leaves = [b.tensor for b in d.boxes]
+c = TreeContraction(CudaCountRel, d.wiring, tree=tree, wire_is_free=free)
+for _ in range(2):
+    assert int(c.contract_from_host(leaves, (lo, hi), all_reduce=True)) == int(brute.sum())
+s = TreeContraction(CudaFinRel, d.wiring, tree=tree)
+assert bool(s.contract_from_host(leaves, (lo, hi), all_reduce=True)) == bool(brute.any())
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok")
 '''
