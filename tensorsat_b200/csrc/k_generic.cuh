@@ -91,17 +91,22 @@ struct SmallOp {
 };
 
 // one small op by the threads of one CTA
-TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
+// (part, n_parts): the outputs of one op can be shared out over several CTAs (the larger ops of a wave); an op that
+// clears its result first (repeated labels) is done by part 0 alone, its barrier being a block barrier
+TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs, int part = 0, int n_parts = 1) {
   const void* lhs = (const uint8_t*)ptrs[d.lhs_buf] + d.lhs_off;
   const void* rhs = d.has_rhs ? (const void*)((const uint8_t*)ptrs[d.rhs_buf] + d.rhs_off) : nullptr;
   void* out = (uint8_t*)ptrs[d.out_buf] + d.out_off;
   if (d.zero_first) {
+    if (part != 0) return;
+    n_parts = 1;
     for (int i = threadIdx.x; i < d.zero_first; i += blockDim.x) store_from_i64(out, d.dout, i, 0);
     __syncthreads();
   }
+  const int first = threadIdx.x + part * blockDim.x, step = blockDim.x * n_parts;
   if (d.binary) {
     // every extent is 2 (all BASELINE networks): index digits are bits, no integer division
-    for (int it = threadIdx.x; it < d.n_out_iter; it += blockDim.x) {
+    for (int it = first; it < d.n_out_iter; it += step) {
       int ol = 0, orr = 0, oo = 0;
       for (int f = d.n_free - 1, q = 0; f >= 0; f--, q++) {
         const int i = (it >> q) & 1;
@@ -126,7 +131,7 @@ TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
     }
     return;
   }
-  for (int it = threadIdx.x; it < d.n_out_iter; it += blockDim.x) {
+  for (int it = first; it < d.n_out_iter; it += step) {
     int ol = 0, orr = 0, oo = 0, rem = it;
     for (int f = d.n_free - 1; f >= 0; f--) {
       const int e = d.ext[f];
@@ -155,11 +160,23 @@ TSB_D void small_op_run(const SmallOp& d, void* const* __restrict__ ptrs) {
   }
 }
 
+// The descriptor is staged in shared memory first: read through a global pointer every field is re-fetched inside the
+// index loops (the compiler must assume the result stores alias it), which made these microsecond-sized ops several
+// times slower than their arithmetic.
+TSB_D void small_op_stage(const SmallOp* __restrict__ src, SmallOp& dst) {
+  static_assert(sizeof(SmallOp) % 4 == 0, "SmallOp is copied word by word");
+  for (int i = threadIdx.x; i < (int)(sizeof(SmallOp) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+  __syncthreads();
+}
+
 static __global__ void __launch_bounds__(kSmallThreads)
 k_small_batch(const SmallOp* __restrict__ ops, void* const* __restrict__ ptrs) {
+  __shared__ SmallOp sd;
   TSB_PDL_TRIGGER();
+  small_op_stage(ops + blockIdx.x, sd);   // descriptors are plan constants: staged before the dependency wait
   TSB_PDL_WAIT();
-  small_op_run(ops[blockIdx.x], ptrs);
+  small_op_run(sd, ptrs, (int)blockIdx.y, (int)gridDim.y);   // gridDim.y CTAs share the outputs of every op of the wave
 }
 
 // A run of consecutive waves that hold one or two small ops each (the vine at the tail of an elimination-order
@@ -170,10 +187,16 @@ constexpr int kChainThreads = 1024;
 
 static __global__ void __launch_bounds__(kChainThreads)
 k_small_chain(const SmallOp* __restrict__ ops, int n_ops, void* const* __restrict__ ptrs) {
+  __shared__ SmallOp sd[2];
   TSB_PDL_TRIGGER();
+  small_op_stage(ops, sd[0]);
   TSB_PDL_WAIT();
   for (int i = 0; i < n_ops; i++) {
-    small_op_run(ops[i], ptrs);
+    if (i + 1 < n_ops) {   // next descriptor into the other buffer while this op runs (visible after the barrier below)
+      for (int w = threadIdx.x; w < (int)(sizeof(SmallOp) / 4); w += blockDim.x)
+        reinterpret_cast<uint32_t*>(&sd[(i + 1) & 1])[w] = reinterpret_cast<const uint32_t*>(ops + i + 1)[w];
+    }
+    small_op_run(sd[i & 1], ptrs);
     __syncthreads();
   }
 }

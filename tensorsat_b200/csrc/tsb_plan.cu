@@ -111,6 +111,7 @@ struct Launch {   // one entry of the once-only schedule
   int batch_begin = 0;  // [begin, end) into the small-op array
   int batch_end = 0;
   bool chain = false;   // the small ops run in order inside one CTA (k_small_chain)
+  int split = 1;        // CTAs per op of a batch (waves that hold the larger small ops)
   float last_ms = 0;
 };
 
@@ -962,6 +963,14 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
       batch.batch_begin = (int)P.small_ops.size();
       for (int i : small[w]) push_small(i);
       batch.batch_end = (int)P.small_ops.size();
+      {
+        // one CTA of 128 threads per op is fine up to a few thousand inner iterations; the larger ops of a wave
+        // (up to 2^17) would otherwise take tens of microseconds on the critical path
+        int64_t work = 0;
+        for (int q = batch.batch_begin; q < batch.batch_end; q++)
+          work = std::max<int64_t>(work, (int64_t)P.small_ops[q].n_out_iter * std::max(1, P.small_ops[q].n_red_iter));
+        batch.split = (int)std::min<int64_t>(32, std::max<int64_t>(1, work / 2048));
+      }
       if (batch.batch_end > batch.batch_begin) sched.push_back(batch);
       for (int i : big[w]) {
         Launch l;
@@ -1424,7 +1433,7 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
         TSB_LAUNCH_PDL(k_small_chain, dim3(1), dim3(kChainThreads), 0, st,
                        (const SmallOp*)(P.d_small_ops + l.batch_begin), n, (void* const*)P.d_ptrs);
       else
-        TSB_LAUNCH_PDL(k_small_batch, dim3(n), dim3(kSmallThreads), 0, st,
+        TSB_LAUNCH_PDL(k_small_batch, dim3(n, l.split), dim3(kSmallThreads), 0, st,
                        (const SmallOp*)(P.d_small_ops + l.batch_begin), (void* const*)P.d_ptrs);
       ctx->note(l.chain ? "k_small_chain" : "k_small_batch");
       TSB_CUDA(cudaGetLastError());
