@@ -292,6 +292,11 @@ int tsb_network_from_clauses(int32_t n_vars, int32_t n_clauses, const int32_t* c
 int tsb_network_from_dimacs(const char* dimacs_text, const char* inputs, tsb_network** net);
 /* Swap the input boxes (assignment search: same wiring, same tree, same plan). */
 int tsb_network_set_inputs(tsb_network* net, const char* inputs);
+/* Unit propagation of the clauses under a partial assignment (spec: '0' / '1' / '?' per variable).  conflict = 1: no
+ * model extends it (sound; not complete: conflict = 0 decides nothing).  out_spec (n_vars + 1 chars, optional)
+ * receives the assignment with the propagated values filled in.  Host only; used by the assignment search to skip
+ * contractions whose answer is implied (notebooks/02-random-ksat.ipynb:707-722 decides every candidate by contraction). */
+int tsb_network_propagate(const tsb_network* net, const char* spec, char* out_spec, int32_t* conflict);
 int tsb_network_info(const tsb_network* net, tsb_network_info_t* info);
 /* Caller-allocated arrays (any may be NULL): leaf_ranks / leaf_kinds [n_leaves], leaf_wires [total_leaf_rank],
  * out_wires [n_out]. */

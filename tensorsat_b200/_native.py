@@ -89,7 +89,7 @@ EXPORTS = [
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
     "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_all_binary", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
     "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",
-    "tsb_plan_destroy", "tsb_network_from_clauses", "tsb_network_from_dimacs", "tsb_network_set_inputs", "tsb_network_info",
+    "tsb_plan_destroy", "tsb_network_from_clauses", "tsb_network_from_dimacs", "tsb_network_set_inputs", "tsb_network_propagate", "tsb_network_info",
     "tsb_network_arrays", "tsb_network_leaf_tensors", "tsb_network_destroy", "tsb_tree_search", "tsb_tree_info",
     "tsb_tree_arrays", "tsb_tree_destroy", "tsb_plan_create_from_tree", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
 ]

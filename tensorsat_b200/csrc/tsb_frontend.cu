@@ -471,6 +471,42 @@ int tsb_network_set_inputs(tsb_network* net, const char* inputs) {
   TSB_FE_END
 }
 
+// Unit propagation of the clauses under a partial assignment: a sound, incomplete filter for the assignment search
+// (a partial assignment refuted by propagation has no model; the contraction stays the complete decision).
+int tsb_network_propagate(const tsb_network* net, const char* spec, char* out_spec, int32_t* conflict) {
+  TSB_FE_BEGIN
+  TSB_CHECK(net && spec && conflict, TSB_ERR_INVALID, "null argument");
+  check_inputs(*net, spec);
+  std::vector<int8_t> val((size_t)net->n_vars);
+  for (int v = 0; v < net->n_vars; v++) val[(size_t)v] = spec[v] == '?' ? -1 : (int8_t)(spec[v] - '0');
+  *conflict = 0;
+  bool changed = true;
+  while (changed && !*conflict) {
+    changed = false;
+    for (const auto& c : net->clauses) {
+      int n_free = 0;
+      int32_t free_lit = 0;
+      bool sat = false;
+      for (auto lit : c) {
+        const int8_t v = val[(size_t)(std::abs(lit) - 1)];
+        if (v < 0) { n_free++; free_lit = lit; }
+        else if ((v == 1) == (lit > 0)) { sat = true; break; }
+      }
+      if (sat) continue;
+      if (n_free == 0) { *conflict = 1; break; }
+      if (n_free == 1) {
+        val[(size_t)(std::abs(free_lit) - 1)] = free_lit > 0 ? 1 : 0;
+        changed = true;
+      }
+    }
+  }
+  if (out_spec) {
+    for (int v = 0; v < net->n_vars; v++) out_spec[v] = val[(size_t)v] < 0 ? '?' : (char)('0' + val[(size_t)v]);
+    out_spec[net->n_vars] = 0;
+  }
+  TSB_FE_END
+}
+
 int tsb_network_info(const tsb_network* net, tsb_network_info_t* info) {
   TSB_FE_BEGIN
   TSB_CHECK(net && info, TSB_ERR_INVALID, "null argument");

@@ -100,6 +100,14 @@ class NativeNetwork:
     def set_inputs(self, inputs: str) -> None:
         _native._check(_native.lib().tsb_network_set_inputs(self._h, _cstr(inputs)))
 
+    def propagate(self, spec: str) -> tuple[bool, str]:
+        """Unit propagation under the partial assignment ``spec``: ``(conflict, spec with implied values filled in)``.
+        A conflict proves that no model extends ``spec``; no conflict proves nothing."""
+        out = C.create_string_buffer(self.info["n_vars"] + 1)
+        conflict = C.c_int32(0)
+        _native._check(_native.lib().tsb_network_propagate(self._h, _cstr(spec), out, C.byref(conflict)))
+        return bool(conflict.value), out.value.decode()
+
     # ---- the flat wiring, as the mirror classes would give it
     def arrays(self) -> tuple[tuple[tuple[int, ...], ...], tuple[int, ...], tuple[int, ...]]:
         """``(slot wire lists, leaf kinds, out wires)``."""

@@ -26,10 +26,20 @@ _BIT = {"0": np.array([1, 0], dtype=np.uint8), "1": np.array([0, 1], dtype=np.ui
 class AssignmentSearch:
     """Decides partial assignments of a CNF formula on one reusable plan and extracts models."""
 
-    def __init__(self, cnf: CNFInstance, contraction: TreeContraction) -> None:
+    def __init__(self, cnf: CNFInstance, contraction: TreeContraction, *, propagate: bool = True) -> None:
+        """``propagate``: let unit propagation (host, ``tsb_network_propagate``) answer the decisions it can — a
+        candidate it refutes is unsatisfiable, and when the other value of the variable is refuted under a
+        satisfiable prefix the candidate is satisfiable — so that only the undetermined candidates cost a
+        contraction.  The decisions and their order are those of the reference either way."""
         if contraction.wiring != cnf.contraction_wiring():
             raise ValueError("The contraction was planned for a different wiring.")
         self._cnf, self._contraction = cnf, contraction
+        self._up = None
+        if propagate:
+            from ..frontend import NativeNetwork
+
+            self._up = NativeNetwork.from_clauses(cnf.num_vars, cnf.clauses)
+        self.implied = 0
         n = cnf.num_vars
         zeros = [b.tensor for b in (cnf.inputs("0" * n) >> cnf.diagram()).flatten().boxes]
         ones = [b.tensor for b in (cnf.inputs("1" * n) >> cnf.diagram()).flatten().boxes]
@@ -56,23 +66,40 @@ class AssignmentSearch:
         decisions, each one execution of the plan."""
         n = self._cnf.num_vars
 
-        def decide(spec: str) -> bool:
-            ok = self.satisfiable(spec)
+        def report(spec: str, ok: bool) -> bool:
             if on_decision is not None:
                 on_decision(spec, ok)
             return ok
+
+        def decide(spec: str, other: str | None = None) -> bool:
+            """``other``: the same prefix with the other value of the variable, given when the prefix is known to
+            be satisfiable (then exactly one refutation settles both candidates)."""
+            if self._up is not None:
+                if self._up.propagate(spec)[0]:
+                    self.implied += 1
+                    return report(spec, False)
+                if other is not None and self._up.propagate(other)[0]:
+                    self.implied += 1
+                    return report(spec, True)
+            return report(spec, self.satisfiable(spec))
 
         if not decide("?" * n):
             return None
         prefix = ""
         for _ in range(n):
             rest = "?" * (n - len(prefix) - 1)
-            if decide(prefix + "0" + rest):
+            zero, one = prefix + "0" + rest, prefix + "1" + rest
+            if decide(zero, one):
                 prefix += "0"
+            elif self._up is not None:
+                # `prefix` is satisfiable and 0 is not: 1 is, without a contraction (the reference runs it)
+                self.implied += 1
+                report(one, True)
+                prefix += "1"
             else:
                 # the formula is satisfiable under `prefix`, so if 0 fails 1 must hold: the reference still
-                # runs the check, and so do we (it keeps the trace comparable and costs one execution)
-                if not decide(prefix + "1" + rest):
+                # runs the check, and so does the pure path (it costs one execution)
+                if not decide(one):
                     raise RuntimeError("Inconsistent decisions: neither value extends a satisfiable prefix.")
                 prefix += "1"
         return prefix

@@ -1083,20 +1083,31 @@ def test_first_model_reproduces_the_reference_traces():
     from tensorsat_b200.lib.search import AssignmentSearch
 
     cnf = CNFInstance.random(3, 3, 6, rng=3)
-    search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring()))
-    trace = []
-    assert search.first_model(lambda spec, ok: trace.append((spec, ok))) == "011"
-    assert trace == [("???", True), ("0??", True), ("00?", False), ("01?", True), ("010", False), ("011", True)]
+    for propagate in (False, True):   # pure: every decision is a contraction; default: unit propagation answers what it can
+        search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring()), propagate=propagate)
+        trace = []
+        assert search.first_model(lambda spec, ok: trace.append((spec, ok))) == "011"
+        assert trace == [("???", True), ("0??", True), ("00?", False), ("01?", True), ("010", False), ("011", True)]
+        assert search.decisions + search.implied == 6 and (search.implied > 0) == propagate
     if _native._device == "cuda":
         cnf = CNFInstance.random(4, 20, 195, rng=1)
-        search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2))
-        assert search.first_model() == "10011001000011100101" and search.decisions == 30
+        search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2), propagate=False)
+        trace = []
+        assert search.first_model(lambda spec, ok: trace.append((spec, ok))) == "10011001000011100101" and search.decisions == 30
+        fast = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2))
+        trace2 = []
+        assert fast.first_model(lambda spec, ok: trace2.append((spec, ok))) == "10011001000011100101"
+        assert trace2 == trace and fast.decisions + fast.implied == 30 and fast.decisions <= 10
     n = 11
     cnf = CNFInstance.random(3, n, 44, rng=2)
     brute = O.cnf_brute_force(n, cnf.clauses).reshape(-1)
-    search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2))
     want = format(int(np.flatnonzero(brute)[0]), "b").rjust(n, "0") if brute.any() else None
-    assert search.first_model() == want
+    traces = []
+    for propagate in (False, True):
+        search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, cnf.contraction_wiring(), trials=2), propagate=propagate)
+        traces.append([])
+        assert search.first_model(lambda spec, ok: traces[-1].append((spec, ok))) == want
+    assert traces[0] == traces[1]
     import os
 
     from tests.conftest import GOLDEN

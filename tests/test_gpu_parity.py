@@ -214,3 +214,33 @@ def test_native_front_end_on_device():
                 assert is_satisfiable(f.read(), trials=2, target_log2_size=28) == verdicts[name], name
     cnf = CNFInstance.random(3, 50, 213, rng=0)
     assert is_satisfiable(cnf.to_dimacs(), trials=2, target_log2_size=28) is True   # (same verdict as bench.py's plan)
+
+
+def test_assignment_search_at_n50_needs_a_fifth_of_the_contractions():
+    """notebooks/02-random-ksat.ipynb:707-722 on BASELINE config 1: the lexicographically first model through
+    AssignmentSearch (one plan, graph replays with swapped input leaves).  With unit propagation answering the
+    implied decisions only 15 of the reference's 76 decisions cost a contraction; the model satisfies the formula and
+    is the one the exact counter's self-reduction finds."""
+    from oracle.sharp_sat import count_models
+    from tensorsat_b200.contractions.tree import TreeContraction
+    from tensorsat_b200.lang.fin_rel import CudaFinRel
+    from tensorsat_b200.lib.sat import CNFInstance
+    from tensorsat_b200.lib.search import AssignmentSearch
+    from tensorsat_b200.planner import Network
+    from tensorsat_b200.planner.search import find_tree_elimination
+
+    n = 50
+    cnf = CNFInstance.random(3, n, 213, rng=0)
+    wiring = cnf.contraction_wiring()
+    tree = find_tree_elimination(Network.from_wiring(wiring), trials=6, seed=0).slice_to(28)
+    search = AssignmentSearch(cnf, TreeContraction(CudaFinRel, wiring, tree=tree))
+    trace = []
+    model = search.first_model(lambda spec, ok: trace.append((spec, ok)))
+    assert model is not None and all(any((model[abs(l) - 1] == "1") == (l > 0) for l in c) for c in cnf.clauses)
+    assert len(trace) == search.decisions + search.implied == 76 and search.decisions <= 19
+    for spec, ok in trace[:: 7]:   # spot-check the trace against the exact counter
+        assert ok == (count_models(n, cnf.clauses, {i: int(ch) for i, ch in enumerate(spec) if ch != "?"}) > 0)
+    prefix = ""
+    for _ in range(n):   # the counter's own self-reduction gives the same lexicographically first model
+        prefix += "0" if count_models(n, cnf.clauses, {i: int(ch) for i, ch in enumerate(prefix + "0")}) > 0 else "1"
+    assert prefix == model
