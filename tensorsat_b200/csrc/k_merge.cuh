@@ -113,7 +113,6 @@ struct BitsFOperand {
 
 struct BitsFDesc {
   int32_t R, kbits, n_ops, tile_bits, n_pair, masks;
-  int32_t prefetch, pad_;     // slots whose fetches of the NEXT vector are prefetched into L1 (bit per slot; A/B knob)
   int32_t perm[kBitsMaxOps];  // slot -> index of the caller's operand (slots are sorted by kmask, descending)
   int64_t n_vec;              // work items: 2^(R - 7 - n_pair)
   BitRuns out_lo, out_hi;     // reduced index -> output vector index (the pair wires are holes)

@@ -20,14 +20,6 @@ constexpr int kBitsFThreads = 256;
 
 TSB_HD constexpr int bits_f_mask(int masks, int kb, int o) { return (masks >> (o * kb)) & ((1 << kb) - 1); }
 
-TSB_D void prefetch_l1(const void* p) {
-#ifndef TSB_HOST_EMU
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 // acc = OR over the summed-wire combinations of AND over the operands; x[o][s] holds operand o at the
 // combination s of the summed wires IT holds (s subset of its mask), so combination kk reads x[o][kk & mask_o]
 template <int NOPS, int KB, int MASKS>
@@ -109,22 +101,6 @@ k_merge_bits_f(const __grid_constant__ BitsFDesc d, const __grid_constant__ Bits
 #pragma unroll
         for (int s = 0; s < KK; s++)
           if ((s & ~bits_f_mask(MASKS, KB, o)) == 0) x0[o][s] = q[d.op[o].kw[s]];
-      }
-      if (d.prefetch != 0 && vi + kBitsFThreads < nt) {
-        // the thread's next vector: its fetches are issued as L1 prefetches now (no registers), so that the loads
-        // of the next iteration find their lines on the way instead of starting an L2 round trip
-#pragma unroll
-        for (int o = 0; o < NOPS; o++) {
-          if (d.prefetch >> o & 1) {
-            const uint4* q = base[o] + tab[o][vi + kBitsFThreads];
-#pragma unroll
-            for (int s = 0; s < KK; s++)
-              if ((s & ~bits_f_mask(MASKS, KB, o)) == 0) {
-                prefetch_l1(q + d.op[o].kw[s]);
-                if (NP >= 1 && (d.op[o].held & 1)) prefetch_l1(q + d.op[o].pw[1] + d.op[o].kw[s]);
-              }
-          }
-        }
       }
       uint4* po = outp + tab[NOPS][vi];
       if constexpr (NP == 2) {

@@ -721,10 +721,6 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
   BitsFDesc& d = m.d;
   d = BitsFDesc{};
   d.R = R; d.kbits = KB; d.n_ops = n; d.n_pair = NP;
-  {
-    static const int pf_env = [] { const char* e = getenv("TSB_BITSF_PREFETCH"); return e ? atoi(e) : 0; }();  // A/B knob
-    d.prefetch = pf_env;
-  }
   const int vr = vb - NP;  // reduced vector-index bits
   static const int tile_env = [] { const char* e = getenv("TSB_BITSF_TILE_BITS"); return e ? atoi(e) : kMergeTileBits; }();  // A/B knob
   d.tile_bits = std::min(vr, std::min(std::min(kMergeTileBits, std::max(tile_env, 6)), std::max(8, vr - 10)));
