@@ -16,7 +16,7 @@ from typing import Any, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtsb.so")
+LIB_PATH = os.environ.get("TSB_LIB") or os.path.join(_HERE, "csrc", "libtsb.so")   # TSB_LIB: A/B builds of the library
 
 TSB_U8, TSB_I32, TSB_I64 = 0, 1, 2
 MODE_SAT, MODE_COUNT = 0, 1

@@ -136,6 +136,14 @@ struct HeldBlocks {
   std::vector<void*> owned;
   std::multimap<size_t, void*> free;
 };
+// Capture state of the CALLING THREAD (a capture runs synchronously inside one tsb_plan_execute call): where the
+// temporaries of the launches go, and where their per-kernel counts are recorded.  Thread-local, so that another
+// thread's direct execution on the same context is not diverted into somebody's graph.
+struct CaptureState {
+  HeldBlocks* hold = nullptr;
+  std::map<std::string, int64_t>* counts = nullptr;
+};
+CaptureState& capture_state();   // tsb_ops.cu
 
 }  // namespace tsb
 
@@ -151,11 +159,9 @@ struct tsb_ctx {
   void note(const char* kernel) {
     launches++;
     if (trace) kcount[kernel]++;
-    if (cap_counts) (*cap_counts)[kernel]++;
+    if (auto* c = tsb::capture_state().counts) (*c)[kernel]++;
   }
   tsb::Arena arena;
-  tsb::HeldBlocks* hold = nullptr;                 // set while a plan execution is captured into a CUDA graph
-  std::map<std::string, int64_t>* cap_counts = nullptr;  // per-kernel launches of the execution being captured
   int* d_flag = nullptr;  // scratch for all_ones
   uint8_t* d_one = nullptr;  // the u8 scalar 1
 };
@@ -166,26 +172,28 @@ void ctx_unref(tsb_ctx* ctx);  // tsb_ops.cu
 
 // RAII temp buffer from the arena for work enqueued on `stream`.  It is released on the host at scope exit while
 // its kernels may still be in flight: the arena orders any later user on another stream after them (event recorded
-// at release).  While a plan execution is being captured into a CUDA graph (ctx->hold != nullptr) the buffer is
+// at release).  While a plan execution is being captured into a CUDA graph (capture_state().hold != nullptr) the buffer is
 // handed to the graph's owner instead: a replay uses the same addresses, so the memory must stay the graph's.
 struct Temp {
   tsb_ctx* ctx;
   cudaStream_t stream;
   void* p = nullptr;
   size_t size = 0;
+  HeldBlocks* held = nullptr;   // set when the buffer belongs to a capture
   Temp(tsb_ctx* c, size_t bytes, cudaStream_t s) : ctx(c), stream(s) {
-    if (c->hold) {
+    if (HeldBlocks* hold = capture_state().hold) {
       // capture: the launches are recorded in stream order, so a temporary released earlier in the capture can serve a
       // later one; the graph ends up owning each distinct block once
+      held = hold;
       size = tsb::Arena::round_up(bytes);
-      auto it = c->hold->free.lower_bound(size);
-      if (it != c->hold->free.end() && it->first <= size * 2 + (size_t(1) << 20)) {
+      auto it = hold->free.lower_bound(size);
+      if (it != hold->free.end() && it->first <= size * 2 + (size_t(1) << 20)) {
         p = it->second;
         size = it->first;
-        c->hold->free.erase(it);
+        hold->free.erase(it);
       } else {
         p = c->arena.alloc(bytes, tsb::Arena::no_stream());
-        c->hold->owned.push_back(p);
+        hold->owned.push_back(p);
       }
       return;
     }
@@ -193,7 +201,7 @@ struct Temp {
   }
   ~Temp() {
     if (!p) return;
-    if (ctx->hold) ctx->hold->free.emplace(size, p);
+    if (held) held->free.emplace(size, p);
     else ctx->arena.release(p, stream);
   }
   Temp(const Temp&) = delete;

@@ -348,6 +348,11 @@ void rewire_impl(tsb_ctx* ctx, const void* src, int src_rank, const int32_t* sex
   launch_generic(ctx, g, sp, nullptr, dst, stream);
 }
 
+CaptureState& capture_state() {
+  static thread_local CaptureState st;
+  return st;
+}
+
 void ctx_unref(tsb_ctx* ctx) {
   if (!ctx || --ctx->refs > 0) return;
   if (ctx->d_flag) cudaFree(ctx->d_flag);

@@ -1635,16 +1635,15 @@ bool execute_as_graph(tsb_plan& P, const void* const* leaf_ptrs, int64_t slice_b
     if (!P.cap_stream && cudaStreamCreateWithFlags(&P.cap_stream, cudaStreamNonBlocking) != cudaSuccess) P.cap_stream = nullptr;
     bool ok = P.cap_stream && cudaStreamBeginCapture(P.cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
-      ctx->hold = &e.held;
-      ctx->cap_counts = &e.kcount;
+      capture_state().hold = &e.held;
+      capture_state().counts = &e.kcount;
       try {
         enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, own_result ? P.gres : out, mask,
                           P.cap_stream, false, graph_streams);
       } catch (const tsb::Error&) {
         ok = false;
       }
-      ctx->hold = nullptr;
-      ctx->cap_counts = nullptr;
+      capture_state() = CaptureState{};
       if (cudaStreamEndCapture(P.cap_stream, &graph) != cudaSuccess || graph == nullptr) ok = false;
     }
     if (ok && cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) ok = false;
@@ -1720,15 +1719,17 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
       // as the plan lives (the caller's replays use the same addresses), and no event may be recorded
       if (!P.gblock) P.gblock = ctx->arena.alloc((size_t)std::max<int64_t>(P.info.peak_bytes, 256));
       static tsb::HeldBlocks forever;      // temporaries of caller-captured launches stay theirs (recycled in capture order)
-      ctx->hold = &forever;
+      static std::mutex forever_mu;
+      std::lock_guard<std::mutex> forever_lock(forever_mu);
+      capture_state().hold = &forever;
       try {
         upload_ptrs(P, (uint8_t*)P.gblock, out, leaf_ptrs, stream);
         enqueue_execution(P, (uint8_t*)P.gblock, leaf_ptrs, slice_begin, slice_end, out, mask, stream, false, 0);
       } catch (...) {
-        ctx->hold = nullptr;
+        capture_state().hold = nullptr;
         throw;
       }
-      ctx->hold = nullptr;
+      capture_state().hold = nullptr;
       return TSB_OK;
     }
 #endif
