@@ -188,8 +188,8 @@ class TreeContraction(Contraction):
         # one pass over the leaves: C-order bytes of every array, joined (uint8 / bool arrays are taken as they
         # are; anything else, or a leaf of another size, shows as a length mismatch and takes the checked path)
         try:
-            blob = b"".join([a.tobytes() for a in leaves])
-        except AttributeError:   # not numpy arrays
+            blob = bytearray().join(leaves)   # buffer protocol: no per-leaf bytes object (C-contiguous arrays only)
+        except (TypeError, BufferError, ValueError):   # not buffers, or not contiguous
             blob = b""
         if len(blob) != pin.numel():
             if [int(np.asarray(a).size) for a in leaves] != sizes:

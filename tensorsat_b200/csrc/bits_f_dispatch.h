@@ -20,15 +20,15 @@ constexpr bool bits_f_sorted(int masks, int kb, int nops) {
 // other build of these sources loaded into the same process (the test suite loads the emulated build too)
 namespace {
 
-template <int NOPS, int KB, int NP, int MASKS>
+template <int NOPS, int KB, int NP, int NT, int MASKS>
 constexpr BitsFKernel bits_f_entry() {
-  if constexpr (bits_f_sorted(MASKS, KB, NOPS)) return k_merge_bits_f<NOPS, KB, MASKS, NP>;
+  if constexpr (bits_f_sorted(MASKS, KB, NOPS)) return k_merge_bits_f<NOPS, KB, MASKS, NP, NT>;
   else return nullptr;
 }
 
-template <int NOPS, int KB, int NP, int... I>
+template <int NOPS, int KB, int NP, int NT = 0, int... I>
 inline BitsFKernel bits_f_lookup(int masks, std::integer_sequence<int, I...>) {
-  static const BitsFKernel table[] = {bits_f_entry<NOPS, KB, NP, I>()...};
+  static const BitsFKernel table[] = {bits_f_entry<NOPS, KB, NP, NT, I>()...};
   return table[masks];
 }
 
@@ -36,14 +36,25 @@ template <int NOPS, int KB>
 inline BitsFKernel bits_f_kernel(int masks, int n_pair) {
   constexpr int N = 1 << (KB * NOPS);
   auto seq = std::make_integer_sequence<int, N>{};
-  return n_pair == 0 ? bits_f_lookup<NOPS, KB, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 1>(masks, seq);
+  return n_pair == 0 ? bits_f_lookup<NOPS, KB, 0, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 1, 0>(masks, seq);
 }
 
-// the four-vector (two pair wires, Gray order) instantiations: one translation unit per group that has them
+// the private-streaming instantiations (two / three pair wires held by slot 0 only): one translation unit per group
+// n_pair in {2, 3}, one-sided
 template <int NOPS, int KB>
-inline BitsFKernel bits_f_kernel_np2(int masks) {
+inline BitsFKernel bits_f_kernel_np2(int masks, int n_pair) {
   constexpr int N = 1 << (KB * NOPS);
-  return bits_f_lookup<NOPS, KB, 2>(masks, std::make_integer_sequence<int, N>{});
+  auto seq = std::make_integer_sequence<int, N>{};
+  return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 0>(masks, seq);
+}
+
+// the two-sided forms, (n_pair, n_pair2) in {2, 3} x {1, 2}: translation units of their own (groups with two summed wires)
+template <int NOPS, int KB>
+inline BitsFKernel bits_f_kernel_two(int masks, int n_pair, int n_pair2) {
+  constexpr int N = 1 << (KB * NOPS);
+  auto seq = std::make_integer_sequence<int, N>{};
+  if (n_pair2 == 1) return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 1>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 1>(masks, seq);
+  return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 2>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 2>(masks, seq);
 }
 
 }  // namespace
@@ -52,9 +63,12 @@ inline BitsFKernel bits_f_kernel_np2(int masks) {
 BitsFKernel bits_f_kernel_4_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_3_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_small(int nops, int kb, int masks, int n_pair);  // everything else
-BitsFKernel bits_f_kernel_np2_4_2(int masks);   // n_pair = 2 exists for the (4, 2), (3, 2), (4, 1), (3, 1) groups only
-BitsFKernel bits_f_kernel_np2_3_2(int masks);
-BitsFKernel bits_f_kernel_np2_x_1(int nops, int masks);
+BitsFKernel bits_f_kernel_np2_4_2(int masks, int n_pair);   // n_pair = 2, 3 exist for the (4, 2), (3, 2), (4, 1), (3, 1) groups only
+BitsFKernel bits_f_kernel_np2_3_2(int masks, int n_pair);
+BitsFKernel bits_f_kernel_two_4_2(int masks, int n_pair, int n_pair2);   // two-sided: (4, 2) and (3, 2) only
+BitsFKernel bits_f_kernel_two_3_2(int masks, int n_pair, int n_pair2);
+BitsFKernel bits_f_kernel_np2_x_1(int nops, int masks, int n_pair);
 inline bool bits_f_has_np2(int nops, int kb) { return (nops == 3 || nops == 4) && (kb == 1 || kb == 2); }
+inline bool bits_f_has_two_sided(int nops, int kb) { return (nops == 3 || nops == 4) && kb == 2; }
 
 }  // namespace tsb

@@ -101,22 +101,24 @@ struct BitsNPtrs {
 // descriptor of the factored fused merge (k_merge_bits_f.cuh): summed-wire masks known at compile time,
 // optionally one "pair" output wire handled per thread so that operands that do not hold it are fetched once
 constexpr int kBitsFMaxKB = 2;
-constexpr int kBitsFMaxPair = 2;
+constexpr int kBitsFMaxPair = 3;
 
 struct BitsFOperand {
   BitRuns lo, hi;   // reduced vector-in-tile index / reduced tile index -> operand offset (entries)
   uint32_t kw[4];   // offset, in 16-byte units, of summed-wire combination kk (wires the operand lacks add 0)
-  uint32_t pw[4];   // offset, in 16-byte units, of pair-wire combination g
+  uint32_t pw[8];   // offset, in 16-byte units, of combination g of the pair wires THIS operand holds
   int32_t kmask;    // summed wires the operand holds
   int32_t held;     // pair wires the operand holds
 };
 
 struct BitsFDesc {
   int32_t R, kbits, n_ops, tile_bits, n_pair, masks;
+  int32_t n_pair2, pad_;      // private streaming: pair wires private to slot 1 (two-sided form), else 0
   int32_t perm[kBitsMaxOps];  // slot -> index of the caller's operand (slots are sorted by kmask, descending)
-  int64_t n_vec;              // work items: 2^(R - 7 - n_pair)
+  int64_t n_vec;              // work items: 2^(R - 7 - n_pair - n_pair2)
   BitRuns out_lo, out_hi;     // reduced index -> output vector index (the pair wires are holes)
-  uint32_t ow[4];             // output vector offset of pair-wire combination g
+  uint32_t ow[8];             // output vector offset of pair-wire combination g (private streaming: of slot 0's wires)
+  uint32_t ow2[4];            // ... of combination h of slot 1's private wires
   BitsFOperand op[kBitsMaxOps];
 };
 

@@ -646,6 +646,12 @@ struct BitsFArgs {
   long wf_chosen = 0, wf_default = 0;  // modelled L1 wavefronts per work item: chosen lane wires / output bits 8..11
 };
 
+inline bool bits_f_sorted_host(int masks, int kb, int nops) {
+  for (int o = 0; o + 1 < nops; o++)
+    if (((masks >> (o * kb)) & ((1 << kb) - 1)) < ((masks >> ((o + 1) * kb)) & ((1 << kb) - 1))) return false;
+  return true;
+}
+
 inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const BitLabels& out_bits, int max_pair,
                                   int n_top_excluded = 0, bool choose_lanes = false, int choose_tile = 0) {
   BitsFArgs m;
@@ -685,58 +691,109 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
     for (int q = 0; q < KB; q++) if (lp[o].count(ks[q])) kmask[o] |= 1 << q;
     slot[o] = o;
   }
-  std::stable_sort(slot.begin(), slot.end(), [&](int a, int b) { return kmask[a] > kmask[b]; });
   // pair labels: output positions >= 8 (vector bit >= 1 keeps the two 16-byte stores of a lane pair in one sector)
   const int vb = R - 7;
-  std::vector<int> pair_pos;
-  std::vector<int> loads(n);
-  for (int o = 0; o < n; o++) loads[o] = 1 << __builtin_popcount((unsigned)kmask[o]);
-  // two pair wires (four vectors per work item) exist for the three- and four-operand groups with summed wires
-  const int pair_cap = std::min(std::min(max_pair, kBitsFMaxPair), ((n == 3 || n == 4) && (KB == 1 || KB == 2)) ? 2 : 1);
-  while ((int)pair_pos.size() < pair_cap && vb - (int)pair_pos.size() > 8) {
-    int best = -1, best_score = 0;
-    for (int j = 8; j < R - n_top_excluded; j++) {  // the leading (sliced) wires stay index bits: sub-range launches
-      if (std::find(pair_pos.begin(), pair_pos.end(), j) != pair_pos.end()) continue;
-      int score = 0;
-      for (int o = 0; o < n; o++)
-        if (!lp[o].count(out_bits[R - 1 - j])) score += loads[o];
-      if (score > best_score) { best_score = score; best = j; }
+  const int min_env = [] { const char* e = getenv("TSB_BITSF_MIN_ITEMS_LOG2"); return e ? atoi(e) : -1; }();   // (tests: pair wires on small steps)
+  const int min_items = min_env >= 0 ? min_env : 8;
+  // Private streaming (max_pair >= 2, groups that have the kernels): two or three output wires that ONLY one operand
+  // holds, that operand having the largest summed-wire mask.  It goes to slot 0 and is streamed over the pair-wire
+  // combinations while the other operands are fetched once per work item.  Two-sided: a second operand with one or two
+  // private wires of its own goes to slot 1 (if the slots stay sorted by mask); its vectors for the combinations of
+  // those wires are folded in with the rest, and every vector streamed from slot 0 yields 2 / 4 results.  The highest
+  // such wires are taken (the low output wires keep indexing lanes and tiles); the leading (sliced) wires stay index
+  // bits (sub-range launches); at least 2^18 work items are kept (~7 tiles per SM at the smallest tile).
+  int priv = -1, priv2 = -1;
+  std::vector<int> pair_s, pair_t;
+  auto private_wires = [&](int o, int cap) {
+    std::vector<int> mine;
+    for (int j = R - n_top_excluded - 1; j >= 8 && (int)mine.size() < cap; j--) {
+      bool only = lp[o].count(out_bits[R - 1 - j]) > 0;
+      for (int o2 = 0; o2 < n && only; o2++) only = o2 == o || !lp[o2].count(out_bits[R - 1 - j]);
+      if (only) mine.push_back(j);
     }
-    if (best < 0) break;
-    pair_pos.push_back(best);
-    for (int o = 0; o < n; o++)
-      if (lp[o].count(out_bits[R - 1 - best])) loads[o] *= 2;
-  }
-  std::sort(pair_pos.begin(), pair_pos.end());
-  if (pair_pos.size() == 2) {
-    // Two pair wires: exhaustive choice.  In the Gray walk 0, 1, 3, 2 pair wire [0] flips twice, [1] once: per four
-    // vectors an operand is fetched once if it holds neither, twice if only [1], three times if only [0], four
-    // times if both.  Pick the (ordered) pair of output wires with the fewest fetches.
-    static const int times[4] = {1, 3, 2, 4};
-    long best = -1;
-    for (int j0 = 8; j0 < R - n_top_excluded; j0++)
-      for (int j1 = 8; j1 < R - n_top_excluded; j1++) {
-        if (j0 == j1) continue;
-        long cost = 0;
-        for (int o = 0; o < n; o++) {
-          const int held = (lp[o].count(out_bits[R - 1 - j0]) ? 1 : 0) | (lp[o].count(out_bits[R - 1 - j1]) ? 2 : 0);
-          cost += (1L << __builtin_popcount((unsigned)kmask[o])) * times[held];
-        }
-        if (best < 0 || cost < best) { best = cost; pair_pos[0] = j0; pair_pos[1] = j1; }
+    return mine;
+  };
+  if (max_pair >= 2 && (n == 3 || n == 4) && (KB == 1 || KB == 2)) {
+    const int budget = vb - (min_env >= 0 ? min_env : 18);   // pair wires this step can afford
+    const int top = *std::max_element(kmask.begin(), kmask.end());
+    for (int o = 0; o < n; o++) {
+      if (kmask[o] != top) continue;
+      std::vector<int> mine = private_wires(o, std::min(std::min(max_pair, kBitsFMaxPair), budget));
+      if (mine.size() >= 2 && mine.size() > pair_s.size()) { pair_s = mine; priv = o; }
+    }
+    const int two_env = [] { const char* e = getenv("TSB_BITSF_TWO_SIDED"); return e ? atoi(e) : 1; }();   // A/B knob: wires of slot 1 (measured: 1 beats 2 on the n=50 bench)
+    if (priv >= 0 && KB == 2 && two_env > 0) {
+      int second = -1;   // largest mask among the others
+      for (int o = 0; o < n; o++) if (o != priv) second = std::max(second, kmask[o]);
+      std::vector<int> cand_t;
+      for (int o = 0; o < n; o++) {
+        if (o == priv || kmask[o] != second) continue;
+        std::vector<int> mine = private_wires(o, std::min(two_env, 2));
+        if (!mine.empty() && mine.size() > cand_t.size()) { cand_t = mine; priv2 = o; }
       }
+      if (priv2 >= 0) {
+        // split of the budget between the two sides: fewest operand fetches per output vector
+        double rest = 0, best = -1;
+        for (int o = 0; o < n; o++) if (o != priv && o != priv2) rest += 1 << __builtin_popcount((unsigned)kmask[o]);
+        const double f0 = 1 << __builtin_popcount((unsigned)kmask[priv]), f1 = 1 << __builtin_popcount((unsigned)kmask[priv2]);
+        int ba = (int)pair_s.size(), bb = 0;
+        for (int a = 2; a <= (int)pair_s.size(); a++)
+          for (int b = 0; b <= (int)cand_t.size() && a + b <= budget; b++) {
+            const double cost = (f0 * (1 << a) + f1 * (1 << b) + rest) / (double)(1 << (a + b));
+            if (best < 0 || cost < best) { best = cost; ba = a; bb = b; }
+          }
+        pair_s.resize(ba);
+        pair_t.assign(cand_t.begin(), cand_t.begin() + bb);
+        if (bb == 0) priv2 = -1;
+      }
+    }
   }
-  const int NP = (int)pair_pos.size();
+  std::stable_sort(slot.begin(), slot.end(), [&](int a, int b) {
+    if ((a == priv) != (b == priv)) return a == priv;
+    if ((a == priv2) != (b == priv2)) return a == priv2;
+    return kmask[a] > kmask[b];
+  });
+  std::vector<int> pair_pos;
+  if (priv < 0) {
+    // one pair wire, chosen among the output wires by the operand fetches that do not depend on it
+    std::vector<int> loads(n);
+    for (int o = 0; o < n; o++) loads[o] = 1 << __builtin_popcount((unsigned)kmask[o]);
+    if (max_pair >= 1 && vb > min_items) {
+      int best = -1, best_score = 0;
+      for (int j = 8; j < R - n_top_excluded; j++) {  // the leading (sliced) wires stay index bits: sub-range launches
+        int score = 0;
+        for (int o = 0; o < n; o++)
+          if (!lp[o].count(out_bits[R - 1 - j])) score += loads[o];
+        if (score > best_score) { best_score = score; best = j; }
+      }
+      if (best >= 0) pair_pos.push_back(best);
+    }
+  } else {
+    std::sort(pair_s.begin(), pair_s.end());
+    std::sort(pair_t.begin(), pair_t.end());
+    pair_pos = pair_s;
+    pair_pos.insert(pair_pos.end(), pair_t.begin(), pair_t.end());
+  }
+  const int NP = (int)pair_pos.size();   // all pair wires; slot 0's come first
   BitsFDesc& d = m.d;
   d = BitsFDesc{};
-  d.R = R; d.kbits = KB; d.n_ops = n; d.n_pair = NP;
+  d.R = R; d.kbits = KB; d.n_ops = n;
+  d.n_pair = priv < 0 ? NP : (int)pair_s.size();
+  d.n_pair2 = (int)pair_t.size();
   const int vr = vb - NP;  // reduced vector-index bits
   static const int tile_env = [] { const char* e = getenv("TSB_BITSF_TILE_BITS"); return e ? atoi(e) : kMergeTileBits; }();  // A/B knob
-  d.tile_bits = std::min(vr, std::min(std::min(kMergeTileBits, std::max(tile_env, 6)), std::max(8, vr - 10)));
+  // (private streaming does 4 ... 32 vectors per work item: smaller tiles keep at least ~7 tiles per SM)
+  d.tile_bits = std::min(vr, std::min(std::min(kMergeTileBits, std::max(tile_env, 6)), std::max(8, vr - (NP >= 2 ? 11 : 10))));
   d.n_vec = int64_t(1) << vr;
-  for (int g = 0; g < 4; g++) {
+  for (int g = 0; g < 8; g++) {
     uint32_t w = 0;
-    for (int q = 0; q < NP; q++) if (g >> q & 1) w += uint32_t(1) << (pair_pos[q] - 7);
+    for (int q = 0; q < d.n_pair; q++) if (g >> q & 1) w += uint32_t(1) << (pair_pos[q] - 7);
     d.ow[g] = w;
+  }
+  for (int h = 0; h < 4; h++) {
+    uint32_t w = 0;
+    for (int q = 0; q < d.n_pair2; q++) if (h >> q & 1) w += uint32_t(1) << (pair_pos[d.n_pair + q] - 7);
+    d.ow2[h] = w;
   }
   for (int s = 0; s < n; s++) {
     const int o = slot[s];
@@ -749,13 +806,19 @@ inline BitsFArgs make_bits_f_desc(const std::vector<BitLabels>& operands, const 
       for (int q = 0; q < KB; q++) if ((kk >> q & 1) && lp[o].count(ks[q])) a += int64_t(1) << lp[o][ks[q]];
       bo.kw[kk] = (uint32_t)(a >> 7);
     }
-    for (int q = 0; q < NP; q++) if (lp[o].count(out_bits[R - 1 - pair_pos[q]])) bo.held |= 1 << q;
-    for (int g = 0; g < 4; g++) {
+    std::vector<int> mine;   // the pair wires this operand holds, in pair_pos order
+    for (int q = 0; q < NP; q++)
+      if (lp[o].count(out_bits[R - 1 - pair_pos[q]])) { bo.held |= 1 << q; mine.push_back(pair_pos[q]); }
+    for (int g = 0; g < 8; g++) {
       int64_t a = 0;
-      for (int q = 0; q < NP; q++)
-        if ((g >> q & 1) && (bo.held >> q & 1)) a += int64_t(1) << lp[o][out_bits[R - 1 - pair_pos[q]]];
+      for (int q = 0; q < (int)mine.size() && q < 3; q++)
+        if (g >> q & 1) a += int64_t(1) << lp[o][out_bits[R - 1 - mine[q]]];
       bo.pw[g] = (uint32_t)(a >> 7);
     }
+  }
+  if (priv >= 0 && !bits_f_sorted_host(d.masks, KB, n)) {
+    // slot 1's mask is not the second largest after all: one-sided (cannot happen with the choice above)
+    return make_bits_f_desc(operands, out_bits, 1, n_top_excluded, choose_lanes, choose_tile);
   }
   // Which output wires index the 32 lanes of a warp.  A warp-wide 16-byte-per-lane access costs one L1 wavefront
   // per distinct 128-byte line, and these steps are bound by exactly that.  Lane bit 0 stays the lowest vector bit

@@ -39,10 +39,14 @@ void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* pt
   }
   TSB_CHECK(((uintptr_t)o & 15) == 0, TSB_ERR_INVALID, "internal: bit-packed result must be 16-byte aligned");
   BitsFKernel k = nullptr;
-  if (d.n_pair == 2) {
-    TSB_CHECK(bits_f_has_np2(d.n_ops, d.kbits), TSB_ERR_INVALID, "internal: no two-pair-wire kernel for this step");
-    k = d.kbits == 1 ? bits_f_kernel_np2_x_1(d.n_ops, d.masks)
-        : d.n_ops == 4 ? bits_f_kernel_np2_4_2(d.masks) : bits_f_kernel_np2_3_2(d.masks);
+  if (d.n_pair >= 2) {
+    TSB_CHECK(bits_f_has_np2(d.n_ops, d.kbits), TSB_ERR_INVALID, "internal: no private-streaming kernel for this step");
+    TSB_CHECK(d.n_pair2 == 0 || bits_f_has_two_sided(d.n_ops, d.kbits), TSB_ERR_INVALID, "internal: no two-sided kernel for this step");
+    if (d.n_pair2 > 0)
+      k = d.n_ops == 4 ? bits_f_kernel_two_4_2(d.masks, d.n_pair, d.n_pair2) : bits_f_kernel_two_3_2(d.masks, d.n_pair, d.n_pair2);
+    else
+      k = d.kbits == 1 ? bits_f_kernel_np2_x_1(d.n_ops, d.masks, d.n_pair)
+          : d.n_ops == 4 ? bits_f_kernel_np2_4_2(d.masks, d.n_pair) : bits_f_kernel_np2_3_2(d.masks, d.n_pair);
   } else {
     k = d.n_ops == 4 && d.kbits == 2 ? bits_f_kernel_4_2(d.masks, d.n_pair)
         : d.n_ops == 3 && d.kbits == 2 ? bits_f_kernel_3_2(d.masks, d.n_pair)
@@ -52,7 +56,7 @@ void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* pt
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   // tuning knobs (A/B runs): persistent CTAs per SM, shared-memory carve-out (percent; the rest of the 256 KB is L1)
   static const int ctas_env = [] { const char* e = getenv("TSB_BITSF_CTAS"); return e ? atoi(e) : 0; }();
-  const int per_sm = ctas_env > 0 ? ctas_env : (d.n_pair == 1 ? 2 : 3);
+  const int per_sm = ctas_env > 0 ? ctas_env : (d.n_pair == 0 ? 3 : 2);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm));
 #ifndef TSB_HOST_EMU
   static const int carve_env = [] { const char* e = getenv("TSB_BITSF_CARVEOUT"); return e ? atoi(e) : -1; }();

@@ -574,7 +574,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
     const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
     const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
-    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 1.0);  // pair wires of the factored kernel; -1: k_merge_bits_n
+    const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 3.0);  // pair wires of the factored kernel (2, 3: private streaming); -1: k_merge_bits_n
     const int NN0 = (int)P.nodes.size();
     auto bits_desc = [&](POp& op) {
       BitLabels lb = bit_labels(op.lw.data(), (int)op.lw.size(), P.wext.data());
@@ -1261,9 +1261,9 @@ static int fetches_x4(const POp& op) {
   int n = 0;
   for (int s = 0; s < op.fd.n_ops; s++) {
     const int kk = 1 << __builtin_popcount((unsigned)op.fd.op[s].kmask);
-    if (op.fd.n_pair == 2) {   // Gray walk over four vectors: fetched 1 / 3 / 2 / 4 times for held = none / [0] / [1] / both
-      static const int times[4] = {1, 3, 2, 4};
-      n += kk * times[op.fd.op[s].held & 3];
+    if (op.fd.n_pair >= 2) {   // private streaming: slot 0 once per 1 / 2 / 4 vectors, slot 1 per 4 / 8, the others per all of an item's (rounded up)
+      const int sh = s == 0 ? op.fd.n_pair2 : s == 1 ? op.fd.n_pair : op.fd.n_pair + op.fd.n_pair2;
+      n += (4 * kk + (1 << sh) - 1) >> sh;
     } else {
       n += ((4 >> op.fd.n_pair) * kk) << __builtin_popcount((unsigned)op.fd.op[s].held);
     }
@@ -1294,7 +1294,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"wf\":" << op.wf_chosen << ",\"wf_default\":" << op.wf_default << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"n_pair2\":" << (op.use_f ? op.fd.n_pair2 : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"wf\":" << op.wf_chosen << ",\"wf_default\":" << op.wf_default << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {

@@ -523,7 +523,8 @@ def test_bit_packed_plans_give_the_same_solution_tensors(monkeypatch, k, n, m, s
 @pytest.mark.parametrize("n,m,seed,batch,n_out,fuse_k,pair", [
     (22, 90, 6, 13, 6, 2, 2), (22, 92, 2, 11, 9, 2, 2), (24, 100, 6, 15, 5, 2, 2), (24, 96, 4, 12, 7, 2, 2),
     (22, 90, 6, 13, 6, 3, 2), (22, 92, 2, 11, 9, 3, 2), (22, 92, 2, 11, 9, -1, 2),
-    (22, 90, 6, 13, 6, 2, 1), (22, 92, 2, 11, 9, 2, 0), (24, 100, 6, 15, 5, 1, 1), (24, 96, 4, 12, 7, 2, -1)])
+    (22, 90, 6, 13, 6, 2, 1), (22, 92, 2, 11, 9, 2, 0), (24, 100, 6, 15, 5, 1, 1), (24, 96, 4, 12, 7, 2, -1),
+    (24, 96, 4, 12, 7, 2, 3), (26, 106, 5, 14, 5, 2, 3), (22, 90, 3, 14, 5, 2, 2)])
 def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch, n_out, fuse_k, pair):
     """Marginals over a few variables (2^n_out entries, zeros and ones) through sliced plans whose pre, per-slice,
     gathered and post steps all run bit-packed, with broadcast twins: equal to brute force, to the byte plan, and a
@@ -535,8 +536,9 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
     monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
     monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")       # fuse consecutive packed steps whatever their size ...
     monkeypatch.setenv("TSB_FUSE_MAX_K", str(fuse_k))  # ... up to this many summed wires per launch (-1: never)
-    monkeypatch.setenv("TSB_FUSE_PAIR", str(pair))     # pair wires of k_merge_bits_f (-1: k_merge_bits_n only)
-    tile = seed in (2, 4)                              # tile wires chosen by operand footprint (TSB_FUSE_TILE) ...
+    monkeypatch.setenv("TSB_FUSE_PAIR", str(pair))     # pair wires of k_merge_bits_f (-1: k_merge_bits_n only; 2, 3: private streaming)
+    monkeypatch.setenv("TSB_BITSF_MIN_ITEMS_LOG2", "1")  # ... also on steps this small
+    tile = seed in (2, 4) and pair < 3                 # tile wires chosen by operand footprint (TSB_FUSE_TILE) ...
     monkeypatch.setenv("TSB_FUSE_TILE", "1" if tile else "0")
     monkeypatch.setenv("TSB_FUSE_LANES", "0" if (seed, pair) == (6, 1) or tile else "1")   # ... or lane wires by wavefronts
     cnf = CNFInstance.random(3, n, m, rng=seed)
@@ -559,6 +561,8 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
         if flags == 0 and 0 <= fuse_k <= 2:   # the factored kernel takes every fused step with <= 2 summed wires
             fused = [o for o in plan.describe()["ops"] if o["fused"] > 0]
             assert fused and all(o["factored"] == (pair >= 0) for o in fused)
+        if flags == 0 and (pair == 3 or (n, seed) == (22, 3)):   # steps with two / three output wires private to one operand
+            assert max(o["n_pair"] for o in plan.describe()["ops"]) >= (3 if n == 24 else 2)
         if flags == 0 and (n, m, seed) == (24, 100, 6):   # this plan gathers a per-slice result that stays bit-packed
             assert any(o["per_slice"] and o["out_gathered"] and o["out_packed"] for o in plan.describe()["ops"])
         res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
@@ -570,6 +574,45 @@ def test_bit_packed_sliced_plans_partial_outputs(monkeypatch, n, m, seed, batch,
         plan.execute(leaves, b, h, plan.info["n_slices"])
         assert np.array_equal((a | b).cpu().numpy().reshape(want.shape), want)
     assert np.array_equal(got[0], want) and np.array_equal(got[_native.PLAN_NO_PACK], want)
+
+
+@pytest.mark.parametrize("na,nb,nc,n_c,pair,want_pairs", [
+    (3, 2, 9, 9, 3, (3, 2)), (3, 2, 10, 10, 3, (3, 2)), (3, 1, 9, 7, 3, (3, 1)), (3, 2, 9, 9, 3, (3, 0)), (2, 2, 9, 8, 2, (2, 2)),
+    (3, 2, 9, 9, 1, (1, 0))])
+def test_private_streaming_fused_kernel(monkeypatch, na, nb, nc, n_c, pair, want_pairs):
+    """k_merge_bits_f with pair wires private to one operand (slot 0 streamed over 4 / 8 combinations) and the
+    two-sided form (slot 1 holds private wires too): out[a.., b.., c..] = OR_{k1,k2} A[k1,k2,a..,c..] B[k2,k1,b..,c..]
+    C[k1,c..] as one fused launch, against the integer einsum + sign of FinRel._contract2 (fin_rel.py:276-279)."""
+    from tensorsat_b200 import _native
+
+    monkeypatch.setenv("TSB_PACK_MIN_LOG2", "0")
+    monkeypatch.setenv("TSB_FUSE_MIN_LOG2", "0")
+    monkeypatch.setenv("TSB_BITSF_MIN_ITEMS_LOG2", "1")
+    monkeypatch.setenv("TSB_FUSE_PAIR", str(pair))
+    monkeypatch.setenv("TSB_BITSF_TWO_SIDED", "0" if want_pairs == (3, 0) else "2")
+    rng = np.random.default_rng(na * 100 + nb * 10 + nc)
+    aw = list(range(2, 2 + na))
+    bw = list(range(2 + na, 2 + na + nb))
+    cw = list(range(2 + na + nb, 2 + na + nb + nc))
+    inputs = [[0, 1] + aw + cw, [1, 0] + bw + cw, [0] + cw[:n_c]]
+    hi = aw + bw
+    rng.shuffle(hi)
+    out = [int(w) for w in hi] + cw
+    leaves = [(rng.random((2,) * len(ws)) < 0.62).astype(np.uint8) for ws in inputs]
+    plan = _native.Plan(inputs, out, [2] * (2 + na + nb + nc), [(0, 1), (3, 2)], [], mode=_native.MODE_SAT)
+    fused = [o for o in plan.describe()["ops"] if o["kind"] == "bits" and o["fused"] > 0]
+    assert len(fused) == 1 and (fused[0]["n_pair"], fused[0]["n_pair2"]) == want_pairs, [(o["n_pair"], o["n_pair2"]) for o in fused]
+    res = _native.empty(plan.info["out_numel"], _native.MODE_SAT)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+    eq = ",".join("".join(letters[w] for w in ws) for ws in inputs) + "->" + "".join(letters[w] for w in out)
+    want = (np.einsum(eq, *[x.astype(np.int64) for x in leaves]) > 0).astype(np.uint8)
+    assert 0.05 < want.mean() < 0.95
+    dev = [_native.upload(x) for x in leaves]
+    for _ in range(2):   # direct launches, then the captured graph
+        res.zero_()
+        plan.execute(dev, res)
+        assert np.array_equal(res.cpu().numpy().reshape(want.shape), want)
+    plan.close()
 
 
 def test_assignment_search_on_bit_packed_sliced_plan(monkeypatch):
