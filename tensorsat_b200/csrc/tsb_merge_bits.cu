@@ -39,8 +39,10 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
   TSB_CHECK(((uintptr_t)l & 15) == 0 && (!d.has_rhs || ((uintptr_t)r & 15) == 0) && ((uintptr_t)o & 15) == 0, TSB_ERR_INVALID,
             "internal: bit-packed operands must be 16-byte aligned");
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
-  // the general kernel builds its lane tables per CTA: give every CTA a few tiles to amortise that
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + 3) / 4, (int64_t)ctx->sm_count * 8));
+  // the general kernel builds its lane tables per CTA: give every CTA a few tiles to amortise that — unless there are
+  // too few tiles to fill the SMs anyway (the broadcast twins of the once-only schedule are on its critical path)
+  const int64_t fill = (int64_t)ctx->sm_count * 2;
+  const int grid = (int)std::max<int64_t>(1, n_tiles <= fill ? n_tiles : std::min<int64_t>(std::max<int64_t>((n_tiles + 3) / 4, fill), (int64_t)ctx->sm_count * 8));
   if (d.has_rhs && d.kbits <= 1 && (d.nibL & 31) == 31 && (d.nibR & 31) == 31) {
     // word-aligned fast path: both operands hold the five in-word lanes
     const int gw = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
