@@ -572,7 +572,7 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     auto env_or = [](const char* name, double dflt) { const char* e = std::getenv(name); return e ? std::atof(e) : dflt; };
     const double kPackMinLog2 = env_or("TSB_PACK_MIN_LOG2", 20.0);
     const double kExpandMaxLog2 = env_or("TSB_PACK_EXPAND_LOG2", 27.0);  // broadcast twins stay L2-sized
-    const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 22.0);       // fuse across intermediates at least this big
+    const double kFuseMinLog2 = env_or("TSB_FUSE_MIN_LOG2", 18.0);       // fuse across intermediates at least this big (22 -> 18: the small per-slice chain of the n=200 plan, 56 -> 32 launches per slice)
     const int kFuseMaxK = (P.flags & TSB_PLAN_NO_FUSE) ? -1 : (int)env_or("TSB_FUSE_MAX_K", 2.0);
     const int kFusePair = (int)env_or("TSB_FUSE_PAIR", 3.0);  // pair wires of the factored kernel (2, 3: private streaming); -1: k_merge_bits_n
     const int NN0 = (int)P.nodes.size();
@@ -818,6 +818,14 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
         const POp& pr = P.ops[producer[opnd]];
         if (!pr.per_slice && is_post_op(pr) == post) w = std::max(w, pr.wave + 1);
       }
+    op.wave = w;
+  }
+  // per-slice ops: dependency level inside one slice iteration (ops of one level are mutually independent)
+  for (auto& op : P.ops) {
+    if (!op.per_slice) continue;
+    int w = 0;
+    for (int opnd : op.all_operands())
+      if (opnd >= 0 && producer[opnd] >= 0 && P.ops[producer[opnd]].per_slice) w = std::max(w, P.ops[producer[opnd]].wave + 1);
     op.wave = w;
   }
   std::vector<int> pre_ops, post_ops;
@@ -1294,7 +1302,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     os << "{\"kind\":\"" << (op.kind == OP_LEAF ? "leaf" : op.kind == OP_PACK ? "pack" : op.kind == OP_UNPACK ? "unpack" : op.kind == OP_EXPAND ? "expand" : op.kind == OP_STEP ? (op.use_bits ? "bits" : op.use_gemm ? "gemm" : op.use_merge ? "merge" : "generic") : "permute")
        << "\",\"per_slice\":" << (op.per_slice ? 1 : 0) << ",\"post\":" << (plan->nodes[op.out].post ? 1 : 0) << ",\"out_bits\":" << ilog2(std::max<int64_t>(1, o.reg_numel))
        << ",\"dtype\":" << o.dtype << ",\"b\":" << op.b << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
-       << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"n_pair2\":" << (op.use_f ? op.fd.n_pair2 : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"wf\":" << op.wf_chosen << ",\"wf_default\":" << op.wf_default << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
+       << ",\"wave\":" << op.wave << ",\"small\":" << (op.small ? 1 : 0) << ",\"factored\":" << (op.use_f ? 1 : 0) << ",\"n_pair\":" << (op.use_f ? op.fd.n_pair : 0) << ",\"n_pair2\":" << (op.use_f ? op.fd.n_pair2 : 0) << ",\"fetches_x4\":" << fetches_x4(op) << ",\"wf\":" << op.wf_chosen << ",\"wf_default\":" << op.wf_default << ",\"out_gathered\":" << (o.gathered ? 1 : 0) << ",\"out_packed\":" << (o.packed ? 1 : 0) << ",\"fused\":" << op.n_fused << ",\"n_operands\":" << op.n_operands() << ",\"nibL\":" << op.md.nibL << ",\"nibR\":" << op.md.nibR
        << ",\"bytes\":" << op.alg_bytes << ",\"ops\":" << op.alg_ops << ",\"ms\":" << op.last_ms;
     if (op.kind == OP_STEP && op.ow.size() >= 20) {
       auto arr = [&](const char* name, const std::vector<int32_t>& v) {
