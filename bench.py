@@ -512,7 +512,9 @@ def main() -> None:
                               f"mean of {n_ph} L2-flushed executions; slice loop holds only these launches: {only_dominant}"),
                 "phase_ms": acc, "step_ms_in_this_pass": step_ms_phase, "share_of_step": loop_ms / step_ms_phase if step_ms_phase else None,
                 "sum_le_step": bool(loop_ms <= ms_per_step * 1.02),
-                "actual_bound": {"what": "16-byte operand fetches and result stores through L1 (operands are L2-resident broadcast twins)",
+                "actual_bound": {"what": ("16-byte operand fetches and result stores through L1: the busiest unit in the ncu capture (about 40 % of peak after "
+                                          "private streaming halved the fetches); otherwise latency (long_scoreboard) on the streamed operand - the "
+                                          "64 MB result of a slice's first launch is read back by the second - at 16 warps per SM"),
                                  "l1_bytes_per_step": l1_bytes, "achieved_GBps": l1_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms else None,
                                  "peak_GBps": l1_peak, "frac": (l1_bytes / (loop_ms * 1e-3) / 1e9 / l1_peak) if loop_ms else None,
                                  "peak_is": "148 SMs x 128 B/clk x SM clock", "ncu_counters": "l1tex__data_pipe_lsu_wavefronts.sum, lts__t_sectors_srcunit_tex_op_read.sum, smsp__issue_active"},

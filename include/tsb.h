@@ -203,9 +203,14 @@ typedef struct {
  *   TSB_PACK_MIN_LOG2 (20)   steps touching a tensor of at least 2^x entries run bit-packed
  *   TSB_PACK_EXPAND_LOG2 (27) largest broadcast twin of a small operand, log2 entries
  *   TSB_PACK_GATHERED (1)    0: gathered per-slice results are stored as bytes even between packed steps
- *   TSB_FUSE_MIN_LOG2 (22)   consecutive packed steps are fused across intermediates of at least 2^x entries
+ *   TSB_FUSE_MIN_LOG2 (18)   consecutive packed steps are fused across intermediates of at least 2^x entries
  *   TSB_FUSE_MAX_K (2)       summed wires per fused launch (-1: never fuse)
- *   TSB_FUSE_PAIR (1)        pair wires of k_merge_bits_f (0: none, -1: k_merge_bits_n only)
+ *   TSB_FUSE_PAIR (3)        pair wires of k_merge_bits_f: 0 none, 1 one wire chosen by the fetches that do not depend on
+ *                            it, 2 / 3 "private streaming" (up to that many output wires that only ONE operand holds;
+ *                            that operand is streamed over their combinations), -1: k_merge_bits_n only
+ *   TSB_BITSF_TWO_SIDED (1)  private streaming: private wires taken from a SECOND operand as well (0: none, max 2)
+ *   TSB_BITSF_MIN_ITEMS_LOG2 tests only: work items a fused launch keeps when pair wires are taken (default 2^18 for
+ *                            private streaming, 2^8 for one pair wire)
  *   TSB_FUSE_LANES (0)       1: k_merge_bits_f picks the wires that index a warp's lanes by a wavefront model
  *                            (measured 2 % slower on the n=50 bench: off)
  *   TSB_CHAIN_MAX_OPS (2)    waves of at most this many small ops join a single-CTA chain launch (0: off)
