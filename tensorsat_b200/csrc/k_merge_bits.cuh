@@ -11,7 +11,7 @@
 // 2^c bits (c = number of those 7 bits the operand depends on) that the vector touches: ONE load of
 // 4 / 8 / 16 bytes, then an expansion to 128 lanes.  Word-level lanes (bits 5, 6) are register moves;
 // in-word lanes (bits 0..4) go through a 256-entry shared-memory table per operand built once per CTA
-// (two tables when the operand has 4 of the 5 in-word bits), so any of the 128 x 128 lane-mask pairs
+// (an operand with 4 of the 5 in-word bits is expanded by bit duplication instead), so any of the 128 x 128 lane-mask pairs
 // runs on the same code.  Combine: 4 LOP3 per summed-wire combination; one 16-byte store.
 // Bound: HBM at 1/8 byte per entry (algorithmic bytes = (|lhs| + |rhs| + |out|) / 8).
 #pragma once
@@ -34,7 +34,23 @@ struct BitsLane {  // uniform per launch and operand
   int c;    // lanes bits the operand depends on (0..7)
   int c5;   // of which in-word (bits 0..4)
   int hi2;  // mask of word-level bits (output bits 5, 6)
+  int p4;   // c5 == 4: the one in-word lane bit the operand lacks
 };
+
+// 16 bits -> the 32 in-word lanes of an operand that lacks in-word lane bit p: lane e reads bit pext(e, ~(1 << p)),
+// i.e. blocks of 2^p bits are doubled.  Pure ALU (a byte permute for p = 3, shifts and masks below that): the
+// two-table lookup this replaces made a 2^30-entry step of the n=200 plan run at a quarter of the HBM rate.
+TSB_D uint32_t bits_dup16(uint32_t s, int p) {
+  if (p == 4) return s | (s << 16);
+  if (p == 3) return __byte_perm(s, 0, 0x1100);
+  uint32_t t = (s | (s << 8)) & 0x00FF00FFu;   // bytes into 16-bit slots
+  t = (t | (t << 4)) & 0x0F0F0F0Fu;            // nibbles into byte slots
+  if (p == 2) return t * 0x11u;
+  t = (t | (t << 2)) & 0x33333333u;            // bit pairs into nibble slots
+  if (p == 1) return t * 5u;
+  t = (t | (t << 1)) & 0x55555555u;            // bits into pair slots
+  return t * 3u;
+}
 
 TSB_HD BitsLane bits_lane(int nib7) {
   BitsLane l;
@@ -42,10 +58,12 @@ TSB_HD BitsLane bits_lane(int nib7) {
   for (int b = 0; b < 7; b++)
     if (nib7 >> b & 1) { c++; if (b < 5) c5++; }
   l.c = c; l.c5 = c5; l.hi2 = nib7 >> 5;
+  l.p4 = 0;
+  for (int b = 0; b < 5; b++) if (!(nib7 >> b & 1)) l.p4 = b;
   return l;
 }
 
-// lut[t * 256 + b]: the 32 in-word lanes produced by byte t of a sub-chunk whose value is b.
+// lut[b]: the 32 in-word lanes produced by a sub-chunk (at most 8 bits: at most three in-word lanes held) of value b.
 // Built once per CTA and only as far as the kernel will index it (nothing when the operand holds all five
 // in-word lanes, table 0 only when it holds at most three).  `pos` is 32 words of shared scratch.
 TSB_D void bits_build_lut(int nib7, uint32_t* lut, uint32_t* pos) {
@@ -53,10 +71,10 @@ TSB_D void bits_build_lut(int nib7, uint32_t* lut, uint32_t* pos) {
   const int c5 = __popc((unsigned)lo5);
   if (threadIdx.x < 32) pos[threadIdx.x] = (uint32_t)pext_bits(threadIdx.x, lo5, 5);
   __syncthreads();
-  if (c5 == 5) return;
-  const int n = c5 == 4 ? 512 : (1 << (1 << c5));
+  if (c5 >= 4) return;   // all five lanes: used in place; four: bits_dup16
+  const int n = 1 << (1 << c5);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint32_t v = (uint32_t)(i & 255) << (8 * (i >> 8));
+    const uint32_t v = (uint32_t)i;
     uint32_t x = 0;
 #pragma unroll 8
     for (int e = 0; e < 32; e++) x |= ((v >> pos[e]) & 1u) << e;
@@ -64,10 +82,33 @@ TSB_D void bits_build_lut(int nib7, uint32_t* lut, uint32_t* pos) {
   }
 }
 
+// Lane classes known at compile time (k_merge_bits<KB, LCL, LCR>): 0 = anything (decided per launch at run time),
+// 1 = the operand holds all seven lane bits (one 16-byte load, used in place), 2 = it lacks exactly one in-word lane
+// bit and holds both word-level bits (one 8-byte load, four bit duplications).  The run-time form costs ~50
+// instructions per fetch; a 2^30-entry step of the n=200 plan spent 226 instructions per result vector in it.
+TSB_HD int bits_lane_class(int nib7) {
+  if (nib7 == 127) return 1;
+  int c5 = 0;
+  for (int b = 0; b < 5; b++) c5 += nib7 >> b & 1;
+  return (nib7 >> 5) == 3 && c5 == 4 ? 2 : 0;
+}
+
 // X[w] = the 32 lanes of output word w: lane e of word w reads chunk bit pext(w*32+e, nib7)
+template <int LC = 0>
 TSB_D void bits_fetch(const uint32_t* __restrict__ base, uint64_t a, const BitsLane ln, const uint32_t* lut,
                       uint32_t X[4]) {
   const uint32_t* p = base + (a >> 5);
+  if constexpr (LC == 1) {
+    const uint4 t = *(const uint4*)p;
+    X[0] = t.x; X[1] = t.y; X[2] = t.z; X[3] = t.w;
+    return;
+  }
+  if constexpr (LC == 2) {
+    const uint2 t = *(const uint2*)p;
+    X[0] = bits_dup16(t.x & 0xffffu, ln.p4); X[1] = bits_dup16(t.x >> 16, ln.p4);
+    X[2] = bits_dup16(t.y & 0xffffu, ln.p4); X[3] = bits_dup16(t.y >> 16, ln.p4);
+    return;
+  }
   uint32_t e0, e1 = 0, e2 = 0, e3 = 0;
   if (ln.c5 == 5) {
     if (ln.hi2 == 0) { e0 = *p; }
@@ -83,9 +124,9 @@ TSB_D void bits_fetch(const uint32_t* __restrict__ base, uint64_t a, const BitsL
     uint32_t s0 = (uint32_t)v & mask, s1 = (uint32_t)(v >> (1 << ln.c5)) & mask,
              s2 = (uint32_t)(v >> (2 << ln.c5)) & mask, s3 = (uint32_t)(v >> (3 << ln.c5)) & mask;
     if (ln.c5 == 4) {
-      e0 = lut[s0 & 255] | lut[256 + (s0 >> 8)];
-      if (nsub > 1) e1 = lut[s1 & 255] | lut[256 + (s1 >> 8)];
-      if (nsub > 2) { e2 = lut[s2 & 255] | lut[256 + (s2 >> 8)]; e3 = lut[s3 & 255] | lut[256 + (s3 >> 8)]; }
+      e0 = bits_dup16(s0, ln.p4);
+      if (nsub > 1) e1 = bits_dup16(s1, ln.p4);
+      if (nsub > 2) { e2 = bits_dup16(s2, ln.p4); e3 = bits_dup16(s3, ln.p4); }
     } else {
       e0 = lut[s0];
       if (nsub > 1) e1 = lut[s1];
@@ -104,13 +145,13 @@ TSB_D void bits_fetch(const uint32_t* __restrict__ base, uint64_t a, const BitsL
 // bitoffL / bitoffR: where the operand (a slice of a shared tensor) starts inside lhs / rhs.
 // KB = 0 / 1: that many summed wires, every load of a thread's vectors issued before the first use
 // (the steps of a SAT plan sum at most one wire); KB = -1: loop over the 2^kbits combinations.
-template <int KB>
+template <int KB, int LCL = 0, int LCR = 0>
 __global__ void __launch_bounds__(kBitsThreads, KB == 1 ? 3 : 4)
 k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ lhs, uint64_t bitoffL,
              const uint32_t* __restrict__ rhs, uint64_t bitoffR, uint4* __restrict__ out) {
   __shared__ uint32_t tabL[1 << kMergeTileBits], tabR[1 << kMergeTileBits];
   __shared__ int64_t kL[256], kR[256];
-  __shared__ uint32_t lutL[512], lutR[512], posL[32], posR[32];
+  __shared__ uint32_t lutL[256], lutR[256], posL[32], posR[32];
   __shared__ RunsSmem runsL, runsR;
   TSB_PDL_TRIGGER();
   const int nt = 1 << d.tile_bits;
@@ -174,8 +215,8 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
 #pragma unroll
           for (int kk = 0; kk < KK; kk++) {
             if (on[g]) {
-              bits_fetch(lhs, aL[g] + (kk ? sl1 : 0), lnL, lutL, XL[g][kk]);
-              if (has_rhs) bits_fetch(rhs, aR[g] + (kk ? sr1 : 0), lnR, lutR, XR[g][kk]);
+              bits_fetch<LCL>(lhs, aL[g] + (kk ? sl1 : 0), lnL, lutL, XL[g][kk]);
+              if (has_rhs) bits_fetch<LCR>(rhs, aR[g] + (kk ? sr1 : 0), lnR, lutR, XR[g][kk]);
               else XR[g][kk][0] = XR[g][kk][1] = XR[g][kk][2] = XR[g][kk][3] = 0xffffffffu;
             } else {
               XL[g][kk][0] = XL[g][kk][1] = XL[g][kk][2] = XL[g][kk][3] = 0;
@@ -199,8 +240,8 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
 #pragma unroll
           for (int g = 0; g < kBitsG; g++) {
             if (on[g]) {
-              bits_fetch(lhs, aL[g] + sl, lnL, lutL, XL[g]);
-              if (has_rhs) bits_fetch(rhs, aR[g] + sr, lnR, lutR, XR[g]);
+              bits_fetch<LCL>(lhs, aL[g] + sl, lnL, lutL, XL[g]);
+              if (has_rhs) bits_fetch<LCR>(rhs, aR[g] + sr, lnR, lutR, XR[g]);
               else XR[g][0] = XR[g][1] = XR[g][2] = XR[g][3] = 0xffffffffu;
             } else {
               XL[g][0] = XL[g][1] = XL[g][2] = XL[g][3] = 0;

@@ -1,4 +1,6 @@
 // tsb_merge_bits.cu — launchers of the bit-packed boolean merge and of the byte <-> bit conversions.
+#include <type_traits>
+
 #include "lower.h"
 #include "k_merge_bits.cuh"
 
@@ -52,15 +54,29 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
     TSB_CUDA(cudaGetLastError());
     return;
   }
-  if (d.kbits == 0)
-    TSB_LAUNCH_PDL(k_merge_bits<0>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
-               (const uint32_t*)r, bitoff_r, (uint4*)o);
-  else if (d.kbits == 1)
-    TSB_LAUNCH_PDL(k_merge_bits<1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
-               (const uint32_t*)r, bitoff_r, (uint4*)o);
-  else
-    TSB_LAUNCH_PDL(k_merge_bits<-1>, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l,
-               (const uint32_t*)r, bitoff_r, (uint4*)o);
+  // lane classes known at compile time where it pays (k_merge_bits.cuh): a full-lane operand against anything, and
+  // against one that lacks a single in-word lane
+  int cl = bits_lane_class(d.nibL), cr = d.has_rhs ? bits_lane_class(d.nibR) : 0;
+  if (cl == 2 && cr != 1) cl = 0;
+  if (cr == 2 && cl != 1) cr = 0;
+  const int kb = d.kbits <= 1 ? d.kbits : -1;
+  auto go = [&](auto kern) {
+    TSB_LAUNCH_PDL(kern, dim3(grid), dim3(kBitsThreads), 0, stream, d, (const uint32_t*)l, bitoff_l, (const uint32_t*)r, bitoff_r, (uint4*)o);
+  };
+  auto by_class = [&](auto kbc) {
+    constexpr int KBC = decltype(kbc)::value;
+    switch (cl * 3 + cr) {
+      case 1 * 3 + 0: go(k_merge_bits<KBC, 1, 0>); break;
+      case 0 * 3 + 1: go(k_merge_bits<KBC, 0, 1>); break;
+      case 1 * 3 + 1: go(k_merge_bits<KBC, 1, 1>); break;
+      case 1 * 3 + 2: go(k_merge_bits<KBC, 1, 2>); break;
+      case 2 * 3 + 1: go(k_merge_bits<KBC, 2, 1>); break;
+      default: go(k_merge_bits<KBC, 0, 0>); break;
+    }
+  };
+  if (kb == 0) by_class(std::integral_constant<int, 0>{});
+  else if (kb == 1) by_class(std::integral_constant<int, 1>{});
+  else by_class(std::integral_constant<int, -1>{});
   ctx->note("k_merge_bits");
   TSB_CUDA(cudaGetLastError());
 }
