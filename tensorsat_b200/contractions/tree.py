@@ -27,6 +27,11 @@ from ..planner import ContractionTree, Network
 from ..planner.search import find_tree, find_tree_elimination
 from .abc import Contraction
 
+try:   # CPython helper of the binding (leaf packing for contract_from_host); optional, built by tensorsat_b200.build
+    from .. import _tsb_host
+except ImportError:   # pragma: no cover
+    _tsb_host = None
+
 
 class TreeContraction(Contraction):
     """A contraction that executes a whole contraction tree as one device plan."""
@@ -187,15 +192,19 @@ class TreeContraction(Contraction):
         pin, dev, res, sizes, ptrs = st
         # one pass over the leaves: C-order bytes of every array, joined (uint8 / bool arrays are taken as they
         # are; anything else, or a leaf of another size, shows as a length mismatch and takes the checked path)
-        try:
-            blob = bytearray().join(leaves)   # buffer protocol: no per-leaf bytes object (C-contiguous arrays only)
-        except (TypeError, BufferError, ValueError):   # not buffers, or not contiguous
-            blob = b""
-        if len(blob) != pin.numel():
-            if [int(np.asarray(a).size) for a in leaves] != sizes:
-                raise ValueError("Leaf sizes differ from those of the first call.")
-            blob = np.concatenate([np.asarray(a, dtype=np.uint8).reshape(-1) for a in leaves]).tobytes()
-        pin.numpy()[:] = np.frombuffer(blob, dtype=np.uint8)
+        pin_np = pin.numpy()
+        if _tsb_host is not None and _tsb_host.pack_into(leaves, pin_np) == pin.numel():
+            pass   # one pass through the buffer protocol, straight into the pinned buffer (csrc/tsb_pyhost.c)
+        else:
+            try:
+                blob = bytearray().join(leaves)   # buffer protocol: no per-leaf bytes object (C-contiguous arrays only)
+            except (TypeError, BufferError, ValueError):   # not buffers, or not contiguous
+                blob = b""
+            if len(blob) != pin.numel():
+                if [int(np.asarray(a).size) for a in leaves] != sizes:
+                    raise ValueError("Leaf sizes differ from those of the first call.")
+                blob = np.concatenate([np.asarray(a, dtype=np.uint8).reshape(-1) for a in leaves]).tobytes()
+            pin_np[:] = np.frombuffer(blob, dtype=np.uint8)
         dev.copy_(pin, non_blocking=True)
         out = _native.empty(plan.info["out_numel"], self.mode)
         lo, hi = (0, plan.info["n_slices"]) if slice_range is None else slice_range

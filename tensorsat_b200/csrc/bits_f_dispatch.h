@@ -48,13 +48,13 @@ inline BitsFKernel bits_f_kernel_np2(int masks, int n_pair) {
   return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 0>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 0>(masks, seq);
 }
 
-// the two-sided forms, (n_pair, n_pair2) in {2, 3} x {1, 2}: translation units of their own (groups with two summed wires)
-template <int NOPS, int KB>
-inline BitsFKernel bits_f_kernel_two(int masks, int n_pair, int n_pair2) {
+// the two-sided forms, (n_pair, n_pair2) in {2, 3} x {1, 2}: translation units of their own (groups with two summed
+// wires; the four-operand group is split by n_pair2, it is the longest compile of the library)
+template <int NOPS, int KB, int NT>
+inline BitsFKernel bits_f_kernel_two(int masks, int n_pair) {
   constexpr int N = 1 << (KB * NOPS);
   auto seq = std::make_integer_sequence<int, N>{};
-  if (n_pair2 == 1) return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 1>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 1>(masks, seq);
-  return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, 2>(masks, seq) : bits_f_lookup<NOPS, KB, 3, 2>(masks, seq);
+  return n_pair == 2 ? bits_f_lookup<NOPS, KB, 2, NT>(masks, seq) : bits_f_lookup<NOPS, KB, 3, NT>(masks, seq);
 }
 
 }  // namespace
@@ -65,7 +65,8 @@ BitsFKernel bits_f_kernel_3_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_small(int nops, int kb, int masks, int n_pair);  // everything else
 BitsFKernel bits_f_kernel_np2_4_2(int masks, int n_pair);   // n_pair = 2, 3 exist for the (4, 2), (3, 2), (4, 1), (3, 1) groups only
 BitsFKernel bits_f_kernel_np2_3_2(int masks, int n_pair);
-BitsFKernel bits_f_kernel_two_4_2(int masks, int n_pair, int n_pair2);   // two-sided: (4, 2) and (3, 2) only
+BitsFKernel bits_f_kernel_two1_4_2(int masks, int n_pair);   // two-sided, one / two private wires in slot 1: (4, 2) and (3, 2) only
+BitsFKernel bits_f_kernel_two2_4_2(int masks, int n_pair);
 BitsFKernel bits_f_kernel_two_3_2(int masks, int n_pair, int n_pair2);
 BitsFKernel bits_f_kernel_np2_x_1(int nops, int masks, int n_pair);
 inline bool bits_f_has_np2(int nops, int kb) { return (nops == 3 || nops == 4) && (kb == 1 || kb == 2); }

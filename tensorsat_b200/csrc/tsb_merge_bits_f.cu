@@ -43,7 +43,8 @@ void launch_merge_bits_f(tsb_ctx* ctx, const BitsFDesc& d, const void* const* pt
     TSB_CHECK(bits_f_has_np2(d.n_ops, d.kbits), TSB_ERR_INVALID, "internal: no private-streaming kernel for this step");
     TSB_CHECK(d.n_pair2 == 0 || bits_f_has_two_sided(d.n_ops, d.kbits), TSB_ERR_INVALID, "internal: no two-sided kernel for this step");
     if (d.n_pair2 > 0)
-      k = d.n_ops == 4 ? bits_f_kernel_two_4_2(d.masks, d.n_pair, d.n_pair2) : bits_f_kernel_two_3_2(d.masks, d.n_pair, d.n_pair2);
+      k = d.n_ops == 3 ? bits_f_kernel_two_3_2(d.masks, d.n_pair, d.n_pair2)
+          : d.n_pair2 == 1 ? bits_f_kernel_two1_4_2(d.masks, d.n_pair) : bits_f_kernel_two2_4_2(d.masks, d.n_pair);
     else
       k = d.kbits == 1 ? bits_f_kernel_np2_x_1(d.n_ops, d.masks, d.n_pair)
           : d.n_ops == 4 ? bits_f_kernel_np2_4_2(d.masks, d.n_pair) : bits_f_kernel_np2_3_2(d.masks, d.n_pair);

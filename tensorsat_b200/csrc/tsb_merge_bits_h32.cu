@@ -3,5 +3,7 @@
 #include "bits_f_dispatch.h"
 
 namespace tsb {
-BitsFKernel bits_f_kernel_two_3_2(int masks, int n_pair, int n_pair2) { return bits_f_kernel_two<3, 2>(masks, n_pair, n_pair2); }
+BitsFKernel bits_f_kernel_two_3_2(int masks, int n_pair, int n_pair2) {
+  return n_pair2 == 1 ? bits_f_kernel_two<3, 2, 1>(masks, n_pair) : bits_f_kernel_two<3, 2, 2>(masks, n_pair);
+}
 }  // namespace tsb

@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "tensorsat_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libtsb_emu.so")
 SOURCES = ["tsb_ops.cu", "tsb_plan.cu", "tsb_gemm.cu", "tsb_merge_sat.cu", "tsb_merge_gen.cu",
-           "tsb_merge_cnt_88.cu", "tsb_merge_cnt_84.cu", "tsb_merge_cnt_48.cu", "tsb_merge_cnt_44.cu", "tsb_merge_wide.cu", "tsb_merge_bits.cu", "tsb_merge_bits_f.cu", "tsb_merge_bits_f42.cu", "tsb_merge_bits_f32.cu", "tsb_merge_bits_g42.cu", "tsb_merge_bits_g32.cu", "tsb_merge_bits_gx1.cu", "tsb_merge_bits_h42.cu", "tsb_merge_bits_h32.cu", "tsb_frontend.cu"]
+           "tsb_merge_cnt_88.cu", "tsb_merge_cnt_84.cu", "tsb_merge_cnt_48.cu", "tsb_merge_cnt_44.cu", "tsb_merge_wide.cu", "tsb_merge_bits.cu", "tsb_merge_bits_f.cu", "tsb_merge_bits_f42.cu", "tsb_merge_bits_f32.cu", "tsb_merge_bits_g42.cu", "tsb_merge_bits_g32.cu", "tsb_merge_bits_gx1.cu", "tsb_merge_bits_h42.cu", "tsb_merge_bits_i42.cu", "tsb_merge_bits_h32.cu", "tsb_frontend.cu"]
 
 
 def build(force: bool = False) -> str:

@@ -220,3 +220,25 @@ def test_bench_script_is_whole():
     assert not missing, missing
     for fn in ("load_tree", "cpu_sample", "run_reference", "micro_rooflines", "c4_subcube_leg", "main"):
         assert fn in defined
+
+
+def test_host_helper_packs_leaves_like_join():
+    """csrc/tsb_pyhost.c (the CPython helper behind contract_from_host): one pass over the leaves equals the joined
+    C-order bytes; anything it cannot take (non-contiguous, not a buffer, too long) is refused with -1."""
+    import numpy as np
+
+    from tensorsat_b200 import build
+
+    if build.build_host_helper() is None:
+        pytest.skip("no C compiler / Python headers: the pure-Python packing path is used")
+    from tensorsat_b200 import _tsb_host
+
+    rng = np.random.default_rng(5)
+    leaves = [rng.integers(0, 2, size=(2,) * int(r), dtype=np.uint8) for r in rng.integers(0, 4, size=300)]
+    want = b"".join(a.tobytes() for a in leaves)
+    dst = np.zeros(len(want), dtype=np.uint8)
+    assert _tsb_host.pack_into(leaves, dst) == len(want) and dst.tobytes() == want
+    assert _tsb_host.pack_into([a.tobytes() for a in leaves], dst) == len(want) and dst.tobytes() == want
+    assert _tsb_host.pack_into(leaves + [np.zeros((4, 4), np.uint8)[:, ::2]], np.zeros(len(want) + 64, np.uint8)) == -1
+    assert _tsb_host.pack_into(leaves + [3], np.zeros(len(want) + 64, np.uint8)) == -1
+    assert _tsb_host.pack_into(leaves + [np.zeros(8, np.uint8)], dst) == -1

@@ -7,7 +7,7 @@ objs=""
 for f in *.cu; do
   b=${f%.cu}
   case $b in
-    tsb_merge_bits_g32|tsb_merge_bits_g42|tsb_merge_bits_gx1|tsb_merge_bits_h32|tsb_merge_bits_h42|tsb_merge_bits_f32|tsb_merge_bits_f42|tsb_merge_bits_f)
+    tsb_merge_bits_g32|tsb_merge_bits_g42|tsb_merge_bits_gx1|tsb_merge_bits_h32|tsb_merge_bits_h42|tsb_merge_bits_i42|tsb_merge_bits_f32|tsb_merge_bits_f42|tsb_merge_bits_f)
       nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f -o /tmp/${b}_$name.o &
       objs="$objs /tmp/${b}_$name.o" ;;
     *) objs="$objs $b.o" ;;
