@@ -268,9 +268,16 @@ k_merge_bits(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__ l
 // stored broadcast, see tsb_plan.cu): every offset is a multiple of 32 entries, so the kernel works in
 // 32-bit WORD offsets, the word-level lane masks HL / HR (output bits 5, 6) are template parameters and an
 // operand fetch is exactly one 4 / 8 / 16-byte load whose words are used in place.
+// H = 0..3: which of the two word-level lane bits the operand holds (all five in-word lanes held); H = 4: the operand
+// holds both word-level bits and lacks ONE in-word lane bit p4 (8-byte load, each 16-bit quarter doubled block-wise)
 template <int H>
-TSB_D void bits_load_words(const uint32_t* __restrict__ p, uint32_t X[4]) {
-  if constexpr (H == 0) { const uint32_t t = *p; X[0] = X[1] = X[2] = X[3] = t; }
+TSB_D void bits_load_words(const uint32_t* __restrict__ p, uint32_t X[4], int p4 = 0) {
+  if constexpr (H == 4) {
+    const uint2 t = *(const uint2*)p;
+    X[0] = bits_dup16(t.x & 0xffffu, p4); X[1] = bits_dup16(t.x >> 16, p4);
+    X[2] = bits_dup16(t.y & 0xffffu, p4); X[3] = bits_dup16(t.y >> 16, p4);
+  }
+  else if constexpr (H == 0) { const uint32_t t = *p; X[0] = X[1] = X[2] = X[3] = t; }
   else if constexpr (H == 1) { const uint2 t = *(const uint2*)p; X[0] = t.x; X[1] = t.y; X[2] = t.x; X[3] = t.y; }
   else if constexpr (H == 2) { const uint2 t = *(const uint2*)p; X[0] = X[1] = t.x; X[2] = X[3] = t.y; }
   else { const uint4 t = *(const uint4*)p; X[0] = t.x; X[1] = t.y; X[2] = t.z; X[3] = t.w; }
@@ -297,6 +304,7 @@ k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__
   const int64_t n_tiles = d.n_vec >> d.tile_bits;
   const bool acc_out = d.accumulate != 0;
   const uint64_t kwL = KB ? (uint64_t)d.ksL[0] >> 5 : 0, kwR = KB ? (uint64_t)d.ksR[0] >> 5 : 0;
+  const int p4L = HL == 4 ? bits_lane(d.nibL).p4 : 0, p4R = HR == 4 ? bits_lane(d.nibR).p4 : 0;
   int64_t tile = blockIdx.x;
   uint64_t offL = tile < n_tiles ? deposit_warp(runsL, (uint64_t)tile) : 0;
   uint64_t offR = tile < n_tiles ? deposit_warp(runsR, (uint64_t)tile) : 0;
@@ -320,8 +328,8 @@ k_merge_bits_w(const __grid_constant__ MergeDesc d, const uint32_t* __restrict__
         const uint32_t* qr = pR + tabR[on[g] ? vi : 0];
 #pragma unroll
         for (int kk = 0; kk < KK; kk++) {
-          bits_load_words<HL>(ql + (kk ? kwL : 0), XL[g][kk]);
-          bits_load_words<HR>(qr + (kk ? kwR : 0), XR[g][kk]);
+          bits_load_words<HL>(ql + (kk ? kwL : 0), XL[g][kk], p4L);
+          bits_load_words<HR>(qr + (kk ? kwR : 0), XR[g][kk], p4R);
         }
       }
 #pragma unroll

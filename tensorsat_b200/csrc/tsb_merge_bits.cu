@@ -45,6 +45,17 @@ void launch_merge_bits(tsb_ctx* ctx, const MergeDesc& d, const void* l, uint64_t
   // too few tiles to fill the SMs anyway (the broadcast twins of the once-only schedule are on its critical path)
   const int64_t fill = (int64_t)ctx->sm_count * 2;
   const int grid = (int)std::max<int64_t>(1, n_tiles <= fill ? n_tiles : std::min<int64_t>(std::max<int64_t>((n_tiles + 3) / 4, fill), (int64_t)ctx->sm_count * 8));
+  if (d.has_rhs && d.kbits <= 1 && ((d.nibL == 127 && bits_lane_class(d.nibR) == 2) || (d.nibR == 127 && bits_lane_class(d.nibL) == 2))) {
+    // word-aligned fast path, one operand lacking a single in-word lane (too large for a broadcast twin): its fetch is
+    // an 8-byte load whose 16-bit quarters are doubled block-wise in registers
+    const int gw = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);
+    const bool lhs_half = d.nibL != 127;
+    if (d.kbits == 0) { if (lhs_half) bits_w_one<0, 4, 3>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream); else bits_w_one<0, 3, 4>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream); }
+    else { if (lhs_half) bits_w_one<1, 4, 3>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream); else bits_w_one<1, 3, 4>(ctx, d, l, bitoff_l, r, bitoff_r, o, gw, stream); }
+    ctx->note("k_merge_bits_w");
+    TSB_CUDA(cudaGetLastError());
+    return;
+  }
   if (d.has_rhs && d.kbits <= 1 && (d.nibL & 31) == 31 && (d.nibR & 31) == 31) {
     // word-aligned fast path: both operands hold the five in-word lanes
     const int gw = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 8);

@@ -315,6 +315,45 @@ def test_contract2_bits_every_lane_class():
             assert np.array_equal(got, want), (mask, small_first)
 
 
+@pytest.mark.parametrize("nk", [0, 1])
+def test_contract2_bits_one_missing_in_word_lane_takes_the_word_path(nk):
+    """An operand that lacks exactly one in-word lane (and is too large for a broadcast twin in a plan) against a
+    full-lane one: k_merge_bits_w with an 8-byte fetch and block-wise bit doubling, every missing lane, either side."""
+    import torch
+
+    from tensorsat_b200 import _native
+
+    rng = np.random.default_rng(31 + nk)
+    dev = _native.device()
+    R = 10
+    ks = list(range(nk))
+    out_w = list(range(nk, R + nk))
+    full = ks + out_w
+    F = (rng.random((2,) * len(full)) < 0.5).astype(np.uint8)
+    fb = torch.zeros(_native.packed_nbytes(F.size), dtype=torch.uint8, device=dev)
+    _native.pack_bits(torch.from_numpy(F.reshape(-1)).to(dev), fb)
+    for p in range(5):
+        sw = ks + [w for j, w in enumerate(out_w) if R - 1 - j != p]   # output bit p = wire out_w[R - 1 - p]
+        S = (rng.random((2,) * len(sw)) < 0.5).astype(np.uint8)
+        sb = torch.zeros(_native.packed_nbytes(S.size), dtype=torch.uint8, device=dev)
+        _native.pack_bits(torch.from_numpy(S.reshape(-1)).to(dev), sb)
+        for small_first in (True, False):
+            ob = torch.zeros(_native.packed_nbytes(1 << R), dtype=torch.uint8, device=dev)
+            _native.trace(True)
+            try:
+                if small_first:
+                    _native.contract2_bits(sb, sw, fb, full, ob, out_w, R + nk)
+                else:
+                    _native.contract2_bits(fb, full, sb, sw, ob, out_w, R + nk)
+                counts = {k: v for k, v in _native.kernel_counts().items() if v}
+            finally:
+                _native.trace(False)
+            assert counts == {"k_merge_bits_w": 1}, counts
+            want = O.contract2(S, sw, F, full, out_w, mode="sat")
+            got = np.unpackbits(ob.cpu().numpy(), bitorder="little")[: 1 << R].reshape((2,) * R)
+            assert np.array_equal(got, want), (p, small_first)
+
+
 def test_contract2_bits_rejects_what_it_cannot_do():
     import torch
 
