@@ -475,6 +475,25 @@ class Box(Shaped, ABC):
         return res
 
     @classmethod
+    def from_wiring(cls, wiring: "Wiring") -> "Box":
+        """The box of this class that a wiring denotes on its own (tensorsat/diagrams.py:750-775): one spider per
+        wire over the ports attached to it, their product, ports ordered as the slot ports in slot order followed
+        by the out ports."""
+        attached: dict[Wire, list[tuple[int, int]]] = {}   # wire -> (slot or -1 for an out port, port), in that order
+        for slot, ws in enumerate(wiring.slot_wires_list):
+            for port, w in enumerate(ws):
+                attached.setdefault(w, []).append((slot, port))
+        for port, w in enumerate(wiring.out_wires):
+            attached.setdefault(w, []).append((-1, port))
+        wired = [w for w in wiring.wires if w in attached]
+        types = wiring.wire_types
+        res = cls.prod(cls.spider(types[w], len(attached[w])) for w in wired)
+        have = [label for w in wired for label in attached[w]]
+        want = [(slot, port) for slot, ws in enumerate(wiring.slot_wires_list) for port in range(len(ws))]
+        want += [(-1, port) for port in range(len(wiring.out_wires))]
+        return res._rewire([have.index(label) for label in want])
+
+    @classmethod
     def spider(cls, t: Type, num_ports: int) -> "Box":
         if not isinstance(num_ports, int):
             raise TypeError("Number of ports must be an integer.")

@@ -654,6 +654,22 @@ def test_private_streaming_fused_kernel(monkeypatch, na, nb, nc, n_c, pair, want
     plan.close()
 
 
+def test_box_from_wiring():
+    """Box.from_wiring (tensorsat/diagrams.py:750-775): spiders per wire, their product, ports in slot order then out."""
+    from tensorsat_b200.diagrams import Wiring
+
+    bit = FinSet(2)
+    wiring = Wiring(wire_types=[bit, bit, FinSet(3)], slot_wires_list=[(0, 1), (1, 2)], out_wires=(0, 2, 2))
+    box = CudaFinRel.from_wiring(wiring)
+    assert box.shape == (bit, bit, bit, FinSet(3), bit, FinSet(3), FinSet(3))
+    want = np.zeros((2, 2, 2, 3, 2, 3, 3), dtype=np.uint8)
+    for a in range(2):
+        for b in range(2):
+            for c in range(3):
+                want[a, b, b, c, a, c, c] = 1
+    assert np.array_equal(box.tensor, want)
+
+
 def test_assignment_search_on_bit_packed_sliced_plan(monkeypatch):
     """The reference's assignment search (notebooks/02-random-ksat.ipynb:707-722) on one sliced, bit-packed
     plan whose leaves change between executions: every decision must agree with brute force, and the model
