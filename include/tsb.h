@@ -252,6 +252,14 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
  * device tensor of leaf i in its own axis order. */
 int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice_begin,
                      int64_t slice_end, void* out, tsb_stream stream);
+/* The same contraction on HOST buffers (the call a host-language binding makes per contraction: the reference holds
+ * its tensors in host memory, tensorsat/lang/fin_rel.py:328-340).  `host_leaves` holds the u8 0/1 leaves back to back
+ * in slot order, each in its own C order (`leaves_bytes` must equal the sum of the leaf sizes of the plan);
+ * `host_out` receives out_numel elements of out_dtype (`out_bytes` = out_numel * element size).  One host-to-device
+ * copy into a staging buffer the plan owns, the execution, one device-to-host copy, all on `stream`; returns after
+ * the result has arrived (the only synchronisation).  Pinned host memory keeps both copies asynchronous. */
+int tsb_plan_execute_host(tsb_plan* plan, const void* host_leaves, size_t leaves_bytes, int64_t slice_begin,
+                          int64_t slice_end, void* host_out, size_t out_bytes, tsb_stream stream);
 /* Timing of executions (device time, CUDA events on the launching stream), reported by tsb_plan_describe:
  *   1: an event pair and a host synchronisation around EVERY launch ("ms" per op; serialises the launches and
  *      removes their overlap: per-op shares for tools, not for totals);

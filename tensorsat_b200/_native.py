@@ -88,7 +88,7 @@ EXPORTS = [
     "tsb_arena_reserve", "tsb_arena_alloc", "tsb_arena_release", "tsb_arena_alloc_async", "tsb_arena_release_async", "tsb_arena_trim", "tsb_arena_stats",
     "tsb_permute", "tsb_rewire", "tsb_contract2", "tsb_slice", "tsb_stack", "tsb_union", "tsb_spider",
     "tsb_fill", "tsb_convert", "tsb_all_ones", "tsb_all_binary", "tsb_scalar_to_host", "tsb_plan_create", "tsb_plan_info",
-    "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_set_timing", "tsb_plan_timing_json",
+    "tsb_plan_describe", "tsb_plan_execute", "tsb_plan_execute_host", "tsb_plan_set_timing", "tsb_plan_timing_json",
     "tsb_plan_destroy", "tsb_network_from_clauses", "tsb_network_from_dimacs", "tsb_network_set_inputs", "tsb_network_propagate", "tsb_network_info",
     "tsb_network_arrays", "tsb_network_leaf_tensors", "tsb_network_destroy", "tsb_tree_search", "tsb_tree_info",
     "tsb_tree_arrays", "tsb_tree_destroy", "tsb_plan_create_from_tree", "tsb_gemm_u8", "tsb_pack_bits", "tsb_unpack_bits", "tsb_contract2_bits",
@@ -408,6 +408,15 @@ class Plan:
             arr = (C.c_void_p * max(1, len(leaf_ptrs)))(*[int(p) for p in leaf_ptrs])
         _check(lib().tsb_plan_execute(self._h, arr, C.c_int64(int(slice_begin)), C.c_int64(int(slice_end)),
                                       C.c_void_p(int(out_ptr)), stream()))
+
+    def execute_host(self, host_leaves_ptr: int, leaves_bytes: int, host_out_ptr: int, out_bytes: int,
+                     slice_begin: int = 0, slice_end: int | None = None) -> None:
+        """``tsb_plan_execute_host``: leaves back to back in host memory in, result in host memory out; returns when
+        the result has arrived."""
+        hi = self.info["n_slices"] if slice_end is None else slice_end
+        _check(lib().tsb_plan_execute_host(self._h, C.c_void_p(int(host_leaves_ptr)), C.c_size_t(int(leaves_bytes)),
+                                           C.c_int64(int(slice_begin)), C.c_int64(int(hi)), C.c_void_p(int(host_out_ptr)),
+                                           C.c_size_t(int(out_bytes)), stream()))
 
     def set_timing(self, enabled: bool | int) -> None:
         """0 / False: off; 1 / True: per-launch (host-synchronised); 2: phase boundaries only (include/tsb.h)."""

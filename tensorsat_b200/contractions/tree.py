@@ -205,15 +205,18 @@ class TreeContraction(Contraction):
                     raise ValueError("Leaf sizes differ from those of the first call.")
                 blob = np.concatenate([np.asarray(a, dtype=np.uint8).reshape(-1) for a in leaves]).tobytes()
             pin_np[:] = np.frombuffer(blob, dtype=np.uint8)
-        dev.copy_(pin, non_blocking=True)
-        out = _native.empty(plan.info["out_numel"], self.mode)
         lo, hi = (0, plan.info["n_slices"]) if slice_range is None else slice_range
-        plan.execute_ptrs(ptrs, out.data_ptr(), lo, hi)
-        if all_reduce:
+        if not all_reduce:
+            # one C-ABI call on host buffers: H2D of the packed leaves, the execution, D2H of the result (tsb_plan_execute_host)
+            plan.execute_host(pin.data_ptr(), pin.numel(), res.data_ptr(), res.numel() * res.element_size(), lo, hi)
+        else:
+            dev.copy_(pin, non_blocking=True)
+            out = _native.empty(plan.info["out_numel"], self.mode)
+            plan.execute_ptrs(ptrs, out.data_ptr(), lo, hi)
             from ..distributed import all_reduce_result
 
             all_reduce_result(out, self.mode, group)
-        res.copy_(out, non_blocking=False)
+            res.copy_(out, non_blocking=False)
         # the plan contracts onto the DISTINCT output wires; repeated output wires tie axes to a diagonal
         # (what contract() does with _rewire; simple.py:287-289)
         dims = tuple(self.wiring.wire_dims[w] for w in self._distinct_out)

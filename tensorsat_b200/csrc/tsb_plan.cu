@@ -153,6 +153,11 @@ struct tsb_plan {
   std::vector<SmallOp> small_ops;      // host copy
   SmallOp* d_small_ops = nullptr;
   uint32_t* d_tabs = nullptr;          // offset tables of the factored fused steps, computed once (bits_f_tables)
+  uint8_t* hx_leaves = nullptr;        // tsb_plan_execute_host: device staging of the leaves (back to back) ...
+  void* hx_out = nullptr;              // ... and of the result
+  size_t hx_total = 0;
+  std::vector<const void*> hx_ptrs;    // leaf pointers into hx_leaves
+  std::mutex hx_mu;                    // one host-buffer execution at a time (they share the staging buffers)
   void** d_ptrs = nullptr;             // device pointer table: [arena, out, leaf 0, leaf 1, ...]
   std::vector<void*> h_ptrs;           // host copy of the table (pageable: the async copy stages it)
   bool mask_root = false;              // root keeps the sliced wires; a final masked sum selects the executed slices
@@ -1755,6 +1760,45 @@ int tsb_plan_execute(tsb_plan* plan, const void* const* leaf_ptrs, int64_t slice
   }
 }
 
+int tsb_plan_execute_host(tsb_plan* plan, const void* host_leaves, size_t leaves_bytes, int64_t slice_begin,
+                          int64_t slice_end, void* host_out, size_t out_bytes, tsb_stream stream_) {
+  try {
+    TSB_CHECK(plan && host_leaves && host_out, TSB_ERR_INVALID, "null argument");
+    tsb_plan& P = *plan;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> host_lock(P.hx_mu);
+    {
+      if (P.hx_ptrs.empty()) {
+        // staging buffers of the host entry point, once per plan: leaves back to back, result
+        size_t total = 0;
+        std::vector<size_t> offs;
+        for (const auto& lw : P.leaf_wires) {
+          offs.push_back(total);
+          total += (size_t)prod_ext(lw, P.wext);
+        }
+        P.hx_total = total;
+        P.hx_leaves = (uint8_t*)P.ctx->arena.alloc(std::max<size_t>(total, 16));
+        P.hx_out = P.ctx->arena.alloc(std::max<size_t>((size_t)P.info.out_numel * dtype_size(P.info.out_dtype), 16));
+        for (size_t o : offs) P.hx_ptrs.push_back(P.hx_leaves + o);
+      }
+    }
+    const size_t want_out = (size_t)P.info.out_numel * dtype_size(P.info.out_dtype);
+    TSB_CHECK(leaves_bytes == P.hx_total, TSB_ERR_INVALID, "host leaves hold %zu bytes, the plan's leaves %zu", leaves_bytes, P.hx_total);
+    TSB_CHECK(out_bytes == want_out, TSB_ERR_INVALID, "host result buffer holds %zu bytes, the plan's result %zu", out_bytes, want_out);
+    TSB_CUDA(cudaMemcpyAsync(P.hx_leaves, host_leaves, leaves_bytes, cudaMemcpyHostToDevice, stream));
+    const int rc = tsb_plan_execute(plan, P.hx_ptrs.data(), slice_begin, slice_end, P.hx_out, stream_);
+    if (rc != TSB_OK) return rc;
+    TSB_CUDA(cudaMemcpyAsync(host_out, P.hx_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+    TSB_CUDA(cudaStreamSynchronize(stream));
+    return TSB_OK;
+  } catch (const tsb::Error& e) {
+    return e.code;
+  } catch (const std::exception& e) {
+    tsb::set_error("internal error: %s", e.what());
+    return TSB_ERR_INVALID;
+  }
+}
+
 int tsb_plan_destroy(tsb_plan* plan) {
   if (plan) {
 #ifndef TSB_HOST_EMU
@@ -1764,6 +1808,8 @@ int tsb_plan_destroy(tsb_plan* plan) {
     try {
       if (plan->gblock) plan->ctx->arena.release(plan->gblock, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
       if (plan->gres) plan->ctx->arena.release(plan->gres, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
+      if (plan->hx_leaves) plan->ctx->arena.release(plan->hx_leaves, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
+      if (plan->hx_out) plan->ctx->arena.release(plan->hx_out, plan->has_last ? plan->last_stream : tsb::Arena::no_stream());
     } catch (...) {
     }
     if (plan->done_ev) cudaEventDestroy(plan->done_ev);

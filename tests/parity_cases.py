@@ -1034,6 +1034,24 @@ def test_contract_from_host_matches_device_leaves():
         assert bool(c.contract_from_host([a.tolist() for a in leaves])) == want
     with pytest.raises(ValueError):
         c.contract_from_host(leaves[:-1])
+    # the C-ABI entry point behind it (tsb_plan_execute_host): sliced, counting semiring, and its size checks
+    tree = find_tree_elimination(Network.from_wiring(wiring), trials=2, seed=0)
+    cc = TreeContraction(CudaCountRel, wiring, tree=tree.slice_to(max(tree.width() - 2, 2)),
+                         wire_is_free=[w < n for w in wiring.wires])
+    flat = (cnf.inputs("?" * n) >> cnf.diagram()).flatten()
+    leaves = [b.tensor for b in flat.boxes]
+    assert cc.num_slices >= 2 and int(cc.contract_from_host(leaves)) == int(brute.sum())
+    h = cc.num_slices // 2
+    assert int(cc.contract_from_host(leaves, (0, h))) + int(cc.contract_from_host(leaves, (h, cc.num_slices))) == int(brute.sum())
+    blob = np.concatenate([a.reshape(-1) for a in leaves]).astype(np.uint8)
+    out = np.zeros(1, dtype=np.int64)
+    plan = cc.plan()
+    plan.execute_host(blob.ctypes.data, blob.size, out.ctypes.data, out.nbytes)      # pageable host memory works too
+    assert int(out[0]) == int(brute.sum())
+    with pytest.raises(ValueError):
+        plan.execute_host(blob.ctypes.data, blob.size - 1, out.ctypes.data, out.nbytes)
+    with pytest.raises(ValueError):
+        plan.execute_host(blob.ctypes.data, blob.size, out.ctypes.data, 4)
 
 
 def test_contract_from_host_with_repeated_output_wires():
