@@ -218,6 +218,9 @@ typedef struct {
  *                            the caller's stream and n side streams (fork / join); measured with 4 on the n=50
  *                            bench: device time -1.5 %, end-to-end time +1.6 % (more host work before the first
  *                            kernel of a step): off
+ *   TSB_SLICE_LANES (0)      two slice lanes: under graph capture the slices alternate between two parallel branches,
+ *                            each with its own copy of the per-slice intermediates (0: for bit-packed plans with at
+ *                            least 12 launches per slice, 1: never, 2: wherever the per-slice ops allow it)
  *   TSB_PRE_RESTRICT (1)     0: a rank computes the once-only tensors in full whatever its slice block
  *   TSB_PERMUTE_T4 (1)       0: never use the 4x4 register-transpose permute kernel */
 

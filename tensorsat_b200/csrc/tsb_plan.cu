@@ -53,6 +53,7 @@ struct PNode {
   bool is_out = false;           // the root, written straight into the caller's buffer
   bool post = false;             // shared node computed AFTER the slice loop (tail of the tree)
   bool gathered = false;         // per-slice node stored with the sliced wires leading: slice s fills block s
+  bool loop_local = false;       // lives only inside one slice iteration (a second slice lane works on a copy)
   bool packed = false;           // boolean relation stored one bit per entry (k_merge_bits.cuh)
   int64_t stored_numel() const { return reg_numel * ((shared || gathered) ? s_numel : 1); }
   std::vector<int32_t> stored() const {  // axis order of the stored buffer
@@ -150,6 +151,9 @@ struct tsb_plan {
   std::vector<Launch> post_schedule;   // once-only part after the slice loop (re-batched tail of the tree)
   std::vector<int> gathered_nodes;     // zero-filled before the slice loop
   std::vector<int> slice_ops;          // per-slice ops, in order
+  int64_t lane_shift = 0;              // > 0: two slice lanes; the loop-local nodes of the second lane live this far up
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t lane_ev[2] = {nullptr, nullptr};
   std::vector<SmallOp> small_ops;      // host copy
   SmallOp* d_small_ops = nullptr;
   uint32_t* d_tabs = nullptr;          // offset tables of the factored fused steps, computed once (bits_f_tables)
@@ -918,6 +922,42 @@ void build_plan(tsb_plan& P, const tsb_plan_desc& D) {
     }
   }
   P.info.peak_bytes = fl.peak;
+  {
+    // Two slice lanes (TSB_SLICE_LANES=2; under graph capture the slices alternate between two parallel branches, so
+    // that the launches of one slice fill the SMs the other leaves idle at its kernel boundaries): every node that
+    // lives only inside one slice iteration gets a second copy above the block.  Only for plans whose per-slice ops
+    // need nothing but their descriptors and the block (no temporaries, no accumulation into the result).
+    // Default (TSB_SLICE_LANES=0): only boolean plans whose slice is a long chain of launches (>= 12: the
+    // n=200 plan has 41, mostly small ones — sub-cube 63.6 -> 54.8 ms); the n=50 plan's slice is four wide launches
+    // that already fill the GPU, and a second copy of its intermediates in flight costs 4 % (L2).  1: never, 2: always.
+    static const int lanes_env = [] { const char* e = getenv("TSB_SLICE_LANES"); return e ? atoi(e) : 0; }();
+    int64_t n_sl = 1;
+    for (auto w : P.sliced) n_sl *= P.wext[w];
+    bool all_bits = P.mode == TSB_SAT;
+    for (int i : P.slice_ops) all_bits = all_bits && (P.ops[i].kind != OP_STEP || P.ops[i].use_bits || P.ops[i].use_merge);
+    const bool want = lanes_env >= 2 || (lanes_env == 0 && all_bits && P.slice_ops.size() >= 12);
+    bool ok = want && sliced_any && L > 1 && !P.stack_out && n_sl >= 2 && !P.slice_ops.empty();
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int i : P.slice_ops) {
+      const POp& op = P.ops[i];
+      const PNode& o = P.nodes[op.out];
+      const bool plain = op.kind == OP_PACK || op.kind == OP_UNPACK || op.kind == OP_EXPAND ||
+                         (op.kind == OP_STEP && !op.use_gemm && (op.use_bits || op.use_merge));
+      ok = ok && plain && !o.is_out && op.out != P.root;
+      if (!o.gathered && !o.is_out && o.offset >= 0) {
+        lo = std::min<int64_t>(lo, o.offset);
+        hi = std::max<int64_t>(hi, o.offset + (int64_t)o.bytes);
+      }
+    }
+    if (ok && hi > lo) {
+      for (int i : P.slice_ops) {
+        PNode& o = P.nodes[P.ops[i].out];
+        if (!o.gathered && !o.is_out && o.offset >= 0) o.loop_local = true;
+      }
+      P.lane_shift = ((P.info.peak_bytes - lo + 255) / 256) * 256;
+      P.info.peak_bytes = hi + P.lane_shift;
+    }
+  }
 
   // ---- launch schedules + small-op table ------------------------------------------------------------
   auto buf_of = [&](int node, int32_t& buf, int64_t& off) {
@@ -1079,8 +1119,10 @@ static void pre_block(const tsb_plan& P, const PNode& nd, int& f_bits, int64_t& 
 }
 
 void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vector<int64_t>* digits, bool accumulate,
-              cudaStream_t stream) {
+              cudaStream_t stream, int64_t lane_off = 0) {
   tsb_ctx* ctx = P.ctx;
+  // address of a node inside the arena block; the second slice lane keeps its own copies of the loop-local nodes
+  auto at = [&](const PNode& x) { return base + x.offset + (x.loop_local ? lane_off : 0); };
   // pre ops of a restricted execution: output sub-block (f bits fewer) and the matching operand sub-blocks
   int fo = 0;
   int64_t oo = 0;
@@ -1101,35 +1143,35 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
         if (fo && (d.n_vec >> fo) >= (int64_t(1) << d.tile_bits) && (oo & 127) == 0) {
           d.n_vec >>= fo;
           P.rr_launches++;
-          launch_merge_bits(ctx, d, base + src.offset, (uint64_t)so, nullptr, 0, base + dst.offset + (oo >> 3), stream);
+          launch_merge_bits(ctx, d, at(src), (uint64_t)so, nullptr, 0, at(dst) + (oo >> 3), stream);
         } else {
-          launch_merge_bits(ctx, d, base + src.offset, 0, nullptr, 0, base + dst.offset, stream);
+          launch_merge_bits(ctx, d, at(src), 0, nullptr, 0, at(dst), stream);
         }
       } else if (op.cv_map) {
         const bool src_packed = op.kind == OP_EXPAND;
         const int64_t n = dst.stored_numel();
         if (fo && (n >> fo) >= 1024 && (oo & 127) == 0 && (!src_packed || (so & 31) == 0) && ++P.rr_launches)
-          launch_pack_map(ctx, base + src.offset + (src_packed ? (so >> 3) : so), src_packed, base + dst.offset + (oo >> 3),
+          launch_pack_map(ctx, at(src) + (src_packed ? (so >> 3) : so), src_packed, at(dst) + (oo >> 3),
                           n >> fo, op.cv_lo, op.cv_hi, stream);
         else
-          launch_pack_map(ctx, base + src.offset, src_packed, base + dst.offset, n, op.cv_lo, op.cv_hi, stream);
+          launch_pack_map(ctx, at(src), src_packed, at(dst), n, op.cv_lo, op.cv_hi, stream);
       } else {
         const int64_t n = src.stored_numel();
         if (fo && (n >> fo) >= 1024 && (oo & 127) == 0 && ++P.rr_launches)
-          launch_pack_bits(ctx, base + src.offset + oo, base + dst.offset + (oo >> 3), n >> fo, stream);
+          launch_pack_bits(ctx, at(src) + oo, at(dst) + (oo >> 3), n >> fo, stream);
         else
-          launch_pack_bits(ctx, base + src.offset, base + dst.offset, n, stream);
+          launch_pack_bits(ctx, at(src), at(dst), n, stream);
       }
       return;
     }
-    void* pd = dst.is_out ? out_ptr : (void*)(base + dst.offset);
+    void* pd = dst.is_out ? out_ptr : (void*)(at(dst));
     if (op.per_slice && dst.gathered) pd = (uint8_t*)pd + shared_offset(P, dst, *digits);
     if (fo && (src.stored_numel() >> fo) >= 1024 && (oo & 127) == 0) {
       P.rr_launches++;
-      launch_unpack_bits(ctx, base + src.offset + (oo >> 3), (uint8_t*)pd + oo, src.stored_numel() >> fo, false, stream);
+      launch_unpack_bits(ctx, at(src) + (oo >> 3), (uint8_t*)pd + oo, src.stored_numel() >> fo, false, stream);
       return;
     }
-    launch_unpack_bits(ctx, base + src.offset, pd, src.stored_numel(), accumulate && dst.is_out, stream);
+    launch_unpack_bits(ctx, at(src), pd, src.stored_numel(), accumulate && dst.is_out, stream);
     return;
   }
   const PNode& a = P.nodes[op.lhs];
@@ -1142,16 +1184,16 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
     const bool sub = fo && op.use_f && (op.fd.n_vec >> fo) >= (int64_t(1) << op.fd.tile_bits) && (oo & 127) == 0;
     for (int j = 0; j < op.n_operands(); j++) {
       const PNode& x = P.nodes[op.operand(j)];
-      ptrs[j] = base + x.offset;
+      ptrs[j] = at(x);
       offs[j] = (op.per_slice && x.shared) ? (uint64_t)shared_offset(P, x, *digits) : sub ? (uint64_t)operand_off(x) : 0;
     }
     // a packed gathered result: slice s fills bit block s
-    uint8_t* po_bits = base + o.offset + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0);
+    uint8_t* po_bits = at(o) + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0);
     if (sub) {
       BitsFDesc d = op.fd;
       d.n_vec >>= fo;
       P.rr_launches++;
-      launch_merge_bits_f(ctx, d, ptrs, offs, base + o.offset + (oo >> 3), stream, op.tab_off >= 0 ? P.d_tabs + op.tab_off : nullptr);
+      launch_merge_bits_f(ctx, d, ptrs, offs, at(o) + (oo >> 3), stream, op.tab_off >= 0 ? P.d_tabs + op.tab_off : nullptr);
     } else if (op.use_f) {
       launch_merge_bits_f(ctx, op.fd, ptrs, offs, po_bits, stream, op.tab_off >= 0 ? P.d_tabs + op.tab_off : nullptr);
     } else {
@@ -1170,27 +1212,27 @@ void run_step(tsb_plan& P, POp& op, uint8_t* base, void* out_ptr, const std::vec
       MergeDesc d = op.md;
       d.n_vec >>= fo;
       P.rr_launches++;
-      launch_merge_bits(ctx, d, base + a.offset, (uint64_t)operand_off(a), base + b.offset, (uint64_t)operand_off(b),
-                        base + o.offset + (oo >> 3), stream);
+      launch_merge_bits(ctx, d, at(a), (uint64_t)operand_off(a), at(b), (uint64_t)operand_off(b),
+                        at(o) + (oo >> 3), stream);
       return;
     }
-    launch_merge_bits(ctx, op.md, base + a.offset, bl, base + b.offset, br,
-                      base + o.offset + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0), stream);
+    launch_merge_bits(ctx, op.md, at(a), bl, at(b), br,
+                      at(o) + ((op.per_slice && o.gathered) ? (shared_offset(P, o, *digits) >> 3) : 0), stream);
     return;
   }
-  const uint8_t* pl = base + a.offset;
-  const uint8_t* pr = base + b.offset;
+  const uint8_t* pl = at(a);
+  const uint8_t* pr = at(b);
   if (op.per_slice) {
     if (a.shared) pl += shared_offset(P, a, *digits) * dtype_size(a.dtype);
     if (b.shared) pr += shared_offset(P, b, *digits) * dtype_size(b.dtype);
   }
-  void* po = o.is_out ? out_ptr : (void*)(base + o.offset);
+  void* po = o.is_out ? out_ptr : (void*)(at(o));
   if (op.per_slice && o.gathered) po = (uint8_t*)po + shared_offset(P, o, *digits) * dtype_size(o.dtype);
   bool acc = accumulate && o.is_out;
   if (P.stack_out && op.out == P.root) {
     // root result goes into the slice's block of the stacked result buffer, accumulating
     const PNode& r = P.nodes[P.rnode];
-    po = base + r.offset + shared_offset(P, r, *digits) * dtype_size(r.dtype);
+    po = at(r) + shared_offset(P, r, *digits) * dtype_size(r.dtype);
     acc = true;
   }
   const bool clamp = P.mode == TSB_SAT;
@@ -1296,7 +1338,7 @@ int tsb_plan_describe(const tsb_plan* plan, char* buf, size_t cap, size_t* neede
     cudaEventElapsedTime(&post, plan->phase_ev[2], plan->phase_ev[3]);
     os << "\"phase_ms\":{\"pre\":" << pre << ",\"slice_loop\":" << loop << ",\"post\":" << post << "},";
   }
-  os << "\"peak_bytes\":" << plan->info.peak_bytes << ",\"n_slices\":" << plan->info.n_slices
+  os << "\"peak_bytes\":" << plan->info.peak_bytes << ",\"slice_lanes\":" << (plan->lane_shift > 0 ? 2 : 1) << ",\"n_slices\":" << plan->info.n_slices
      << ",\"restricted_launches\":" << plan->rr_launches << ",\"graph_captures\":" << plan->n_captures
      << ",\"graph_replays\":" << plan->n_replays << ",\"ops\":[";
   bool first = true;
@@ -1527,6 +1569,14 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
   phase_mark(1);
   // per-slice part
   if (!P.sliced.empty()) {
+    const bool lanes = P.lane_shift > 0 && !timing && n_side_max > 0 && slice_end - slice_begin >= 2;
+    if (lanes) {
+      if (!P.lane_stream) TSB_CUDA(cudaStreamCreateWithFlags(&P.lane_stream, cudaStreamNonBlocking));
+      for (auto& e : P.lane_ev)
+        if (!e) TSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      TSB_CUDA(cudaEventRecord(P.lane_ev[0], stream));
+      TSB_CUDA(cudaStreamWaitEvent(P.lane_stream, P.lane_ev[0], 0));
+    }
     for (int64_t sid = slice_begin; sid < slice_end; sid++) {
       const std::vector<int64_t> digits = slice_digits(P, sid);
       if (P.n_leaves == 1) {
@@ -1546,10 +1596,16 @@ void enqueue_execution(tsb_plan& P, uint8_t* base, const void* const* leaf_ptrs,
                     ports.data(), r.dtype, P.mode == TSB_SAT, true, stream);
         continue;
       }
+      // two lanes: slices alternate between the caller's stream and the plan's lane stream (captured: two branches)
+      const bool second = lanes && ((sid - slice_begin) & 1);
       for (int i : P.slice_ops) {
         POp& op = P.ops[i];
-        timed((size_t)i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, stream); });
+        timed((size_t)i, [&] { run_step(P, op, base, out, &digits, sid != slice_begin, second ? P.lane_stream : stream, second ? P.lane_shift : 0); });
       }
+    }
+    if (lanes) {
+      TSB_CUDA(cudaEventRecord(P.lane_ev[1], P.lane_stream));
+      TSB_CUDA(cudaStreamWaitEvent(stream, P.lane_ev[1], 0));
     }
   }
   phase_mark(2);
@@ -1814,6 +1870,8 @@ int tsb_plan_destroy(tsb_plan* plan) {
     }
     if (plan->done_ev) cudaEventDestroy(plan->done_ev);
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+    if (plan->lane_stream) cudaStreamDestroy(plan->lane_stream);
+    for (auto e : plan->lane_ev) if (e) cudaEventDestroy(e);
     for (auto e : plan->ev) cudaEventDestroy(e);
     for (auto e : plan->phase_ev) if (e) cudaEventDestroy(e);
     for (auto e : plan->side_ev) cudaEventDestroy(e);
