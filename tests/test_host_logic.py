@@ -242,3 +242,19 @@ def test_host_helper_packs_leaves_like_join():
     assert _tsb_host.pack_into(leaves + [np.zeros((4, 4), np.uint8)[:, ::2]], np.zeros(len(want) + 64, np.uint8)) == -1
     assert _tsb_host.pack_into(leaves + [3], np.zeros(len(want) + 64, np.uint8)) == -1
     assert _tsb_host.pack_into(leaves + [np.zeros(8, np.uint8)], dst) == -1
+
+
+def test_two_slice_lanes_on_the_emulated_build():
+    """TSB_SLICE_LANES=2 (slices alternate between two streams, the second with its own copy of the per-slice nodes):
+    the knobs are read once per process, so the sliced packed-plan parity cases run in a child process with them set
+    (TSB_WAVE_STREAMS > 0 lets direct launches fork as a captured graph would)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TSB_SLICE_LANES="2", TSB_WAVE_STREAMS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_emu_parity.py", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "partial_outputs and (24-96-4-12-7-2-3 or 22-90-6-13-6-2-1)"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
